@@ -1,0 +1,581 @@
+// Thin SVD by block one-sided Jacobi on row vectors (Hestenes), batched over
+// same-shape matrices.  Replaces torch.linalg.svd(w, full_matrices=False) at
+// reference modeling_grasp.py:231.
+//
+// Y0 = A (out <= in) or A^T (out > in) is r x L with r = min(out,in).  The working
+// matrix Z = [Y | QT] (r x (L + r), QT = I at start) is rotated from the left,
+// Z <- E^T Z on pairs of b-row blocks, until the rows of Y are mutually orthogonal:
+//   Y = Q^T Y0  =>  Y0 = Q diag(sigma) W^T,  sigma_i = |Y_i|, W^T = rows of Y / sigma.
+// One round = (gram) G = Yp Yp^T for every block pair, (evd) small symmetric
+// Jacobi eigen-solve in shared memory producing E^T, (update) Z_pair <- E^T Z_pair.
+// Rotation angles and the eigenvector accumulation are fp64 (fp32 rotations lose
+// orthogonality ~1e-4 at n=4096); the Gram/updates are fp32.
+#include "common.cuh"
+
+namespace grasp {
+
+constexpr int JB = 32;        // rows per block
+constexpr int JS = 2 * JB;    // rows per pair = order of the small eigenproblem
+constexpr int J_THREADS = 256;
+constexpr int J_MAXMAT = 8;   // matrices per launch group
+constexpr int J_STATS = 64;   // uint32 slots of per-matrix status
+
+struct SvdMat {
+  float* Z;          // [rp][ldz]
+  float* Gpart;      // [npairs][nsplit][JS*JS]
+  float* ET;         // [npairs][JS*JS]
+  int* pair_flag;    // [npairs] 1 = ET is not the identity
+  uint32_t* stats;   // [J_STATS]: [0]=converged flag, [1]=sweeps used, [2]=last maxoff bits, [8+s]=maxoff bits of sweep s
+};
+
+struct SvdGroup {
+  SvdMat mat[J_MAXMAT];
+  int nmat;
+  int rp, Lp, ldz;   // padded rows, padded Y columns, row stride of Z
+  int p;             // number of row blocks (even)
+  int npairs;        // p/2
+  int nsplit;        // K splits of the Gram
+};
+
+// round-robin tournament: pair k of round t among p players
+__device__ __forceinline__ void rr_pair(int p, int t, int k, int& a, int& b) {
+  int x, y;
+  if (k == 0) { x = p - 1; y = t; }
+  else {
+    x = (t + k) % (p - 1);
+    y = (t - k + (p - 1)) % (p - 1);
+  }
+  a = min(x, y);
+  b = max(x, y);
+}
+
+__device__ __forceinline__ const float* pair_row(const float* Z, int ldz, int I, int J, int rr) {
+  const int row = (rr < JB) ? (I * JB + rr) : (J * JB + rr - JB);
+  return Z + (int64_t)row * ldz;
+}
+
+// ---------------------------------------------------------------------------
+// init: Z = [Y0 | I], zero padding.  trans: Y0[i][j] = A[j][i]
+// ---------------------------------------------------------------------------
+__global__ void svd_init_kernel(const float* __restrict__ A, int64_t lda, int r, int L, int trans,
+                                float* __restrict__ Z, int rp, int Lp, int ldz) {
+  __shared__ float tile[32][33];
+  const int j0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  if (j0 < Lp) {
+    if (!trans) {
+      for (int dy = ty; dy < 32; dy += 8) {
+        const int i = i0 + dy, j = j0 + tx;
+        if (i < rp && j < Lp) Z[(int64_t)i * ldz + j] = (i < r && j < L) ? A[(int64_t)i * lda + j] : 0.f;
+      }
+    } else {
+      // A is L x r here (rows of A index j); read coalesced along A's rows, write transposed
+      for (int dy = ty; dy < 32; dy += 8) {
+        const int j = j0 + dy, i = i0 + tx;
+        tile[dy][tx] = (i < r && j < L) ? A[(int64_t)j * lda + i] : 0.f;
+      }
+      __syncthreads();
+      for (int dy = ty; dy < 32; dy += 8) {
+        const int i = i0 + dy, j = j0 + tx;
+        if (i < rp && j < Lp) Z[(int64_t)i * ldz + j] = tile[tx][dy];
+      }
+    }
+  } else {
+    const int jq0 = j0 - Lp;  // QT part
+    for (int dy = ty; dy < 32; dy += 8) {
+      const int i = i0 + dy, j = jq0 + tx;
+      if (i < rp && Lp + j < ldz) Z[(int64_t)i * ldz + Lp + j] = (i == j) ? 1.f : 0.f;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// gram: Gpart[pair][split] = Yp[:, kchunk] Yp[:, kchunk]^T   (64 x 64, fp32 FMA)
+// grid (nsplit, npairs, nmat)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(J_THREADS)
+svd_gram_kernel(SvdGroup g, int round) {
+  const SvdMat& M = g.mat[blockIdx.z];
+  if (M.stats[0]) return;
+  constexpr int KC = 32;
+  __shared__ float Ys[KC][JS + 1];
+  int I, J;
+  rr_pair(g.p, round, blockIdx.y, I, J);
+  const int chunks = g.Lp / KC;
+  const int per = (chunks + g.nsplit - 1) / g.nsplit;
+  const int c_beg = blockIdx.x * per, c_end = min(chunks, c_beg + per);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float acc[4][4] = {};
+  for (int c = c_beg; c < c_end; ++c) {
+    // 64 rows x 32 k: thread -> (row = e / 32, kk = e % 32): 128-byte coalesced row segments
+#pragma unroll
+    for (int it = 0; it < (JS * KC) / J_THREADS; ++it) {
+      const int e = tid + it * J_THREADS;
+      const int rr = e >> 5, kk = e & 31;
+      Ys[kk][rr] = pair_row(M.Z, g.ldz, I, J, rr)[c * KC + kk];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < KC; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = Ys[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Ys[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* out = M.Gpart + ((int64_t)blockIdx.y * g.nsplit + blockIdx.x) * (JS * JS);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[(ty * 4 + i) * JS + tx * 4 + j] = acc[i][j];
+}
+
+// ---------------------------------------------------------------------------
+// evd: parallel-order two-sided Jacobi on the 64x64 Gram of one pair.
+// G (fp32) and E (fp64) live in shared memory; rotation parameters in fp64.
+// grid (npairs, nmat)
+// ---------------------------------------------------------------------------
+struct EvdSmem {
+  float G[JS][JS + 1];
+  double E[JS][JS + 1];
+  double c[JS / 2], s[JS / 2];
+  int pp[JS / 2], qq[JS / 2];
+  float red[32];
+  int rank[JS];
+  int rotated;
+  int nonident;
+};
+
+__global__ void __launch_bounds__(J_THREADS)
+svd_evd_kernel(SvdGroup g, int round, int sweep, float tol, int inner_cap) {
+  const SvdMat& M = g.mat[blockIdx.y];
+  if (M.stats[0]) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  EvdSmem& sm = *reinterpret_cast<EvdSmem*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int pair = blockIdx.x;
+  constexpr int H = JS / 2;
+
+  // G = sum of K-split partials (fixed order => deterministic)
+  const float* gp = M.Gpart + (int64_t)pair * g.nsplit * (JS * JS);
+  for (int e = tid; e < JS * JS; e += J_THREADS) {
+    float v = 0.f;
+    for (int sp = 0; sp < g.nsplit; ++sp) v += gp[(int64_t)sp * (JS * JS) + e];
+    sm.G[e / JS][e % JS] = v;
+    sm.E[e / JS][e % JS] = (e / JS == e % JS) ? 1.0 : 0.0;
+  }
+  if (tid == 0) { sm.rotated = 0; sm.nonident = 0; }
+  __syncthreads();
+  // symmetrise and measure the largest relative off-diagonal
+  float maxoff = 0.f;
+  for (int e = tid; e < JS * JS; e += J_THREADS) {
+    const int i = e / JS, j = e % JS;
+    if (i < j) {
+      const float v = 0.5f * (sm.G[i][j] + sm.G[j][i]);
+      sm.G[i][j] = v;
+      sm.G[j][i] = v;
+      const float d = sm.G[i][i] * sm.G[j][j];
+      if (d > 0.f) maxoff = fmaxf(maxoff, fabsf(v) * rsqrtf(d));
+    }
+  }
+  maxoff = warp_max(maxoff);
+  if ((tid & 31) == 0) sm.red[tid >> 5] = maxoff;
+  __syncthreads();
+  if (tid < 32) {
+    float v = (tid < J_THREADS / 32) ? sm.red[tid] : 0.f;
+    v = warp_max(v);
+    if (tid == 0) {
+      sm.red[0] = v;
+      atomicMax(&M.stats[8 + sweep], __float_as_uint(v));
+    }
+  }
+  __syncthreads();
+  maxoff = sm.red[0];
+
+  if (maxoff >= tol) {
+    for (int isw = 0; isw < inner_cap; ++isw) {
+      if (tid == 0) sm.rotated = 0;
+      __syncthreads();
+      for (int t = 0; t < JS - 1; ++t) {
+        if (tid < H) {
+          int p, q;
+          rr_pair(JS, t, tid, p, q);
+          const double gpp = sm.G[p][p], gqq = sm.G[q][q], gpq = sm.G[p][q];
+          double c = 1.0, s = 0.0;
+          if (gpq != 0.0 && fabs(gpq) > (double)tol * sqrt(fabs(gpp * gqq))) {
+            const double tau = (gqq - gpp) / (2.0 * gpq);
+            const double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+            c = 1.0 / sqrt(1.0 + tt * tt);
+            s = tt * c;
+            sm.rotated = 1;
+            sm.nonident = 1;
+          }
+          sm.c[tid] = c; sm.s[tid] = s; sm.pp[tid] = p; sm.qq[tid] = q;
+        }
+        __syncthreads();
+        // G <- J^T G J on disjoint 2x2 blocks
+        for (int blk = tid; blk < H * H; blk += J_THREADS) {
+          const int k1 = blk / H, k2 = blk % H;
+          const float s1 = (float)sm.s[k1], s2 = (float)sm.s[k2];
+          if (s1 == 0.f && s2 == 0.f) continue;
+          const float c1 = (float)sm.c[k1], c2 = (float)sm.c[k2];
+          const int p1 = sm.pp[k1], q1 = sm.qq[k1], p2 = sm.pp[k2], q2 = sm.qq[k2];
+          const float b00 = sm.G[p1][p2], b01 = sm.G[p1][q2], b10 = sm.G[q1][p2], b11 = sm.G[q1][q2];
+          const float t00 = c1 * b00 - s1 * b10, t01 = c1 * b01 - s1 * b11;
+          const float t10 = s1 * b00 + c1 * b10, t11 = s1 * b01 + c1 * b11;
+          float n00 = c2 * t00 - s2 * t01, n01 = s2 * t00 + c2 * t01;
+          float n10 = c2 * t10 - s2 * t11, n11 = s2 * t10 + c2 * t11;
+          if (k1 == k2) { n01 = 0.f; n10 = 0.f; }
+          sm.G[p1][p2] = n00; sm.G[p1][q2] = n01; sm.G[q1][p2] = n10; sm.G[q1][q2] = n11;
+        }
+        // E <- E J (fp64)
+        for (int it = tid; it < JS * H; it += J_THREADS) {
+          const int k = it % H, i = it / H;
+          const double s = sm.s[k];
+          if (s == 0.0) continue;
+          const double c = sm.c[k];
+          const int p = sm.pp[k], q = sm.qq[k];
+          const double ep = sm.E[i][p], eq = sm.E[i][q];
+          sm.E[i][p] = c * ep - s * eq;
+          sm.E[i][q] = s * ep + c * eq;
+        }
+        __syncthreads();
+      }
+      if (!sm.rotated) break;
+      __syncthreads();
+    }
+  }
+
+  // order the new rows by descending squared norm (diag of the rotated Gram)
+  if (tid < JS) {
+    const float di = sm.G[tid][tid];
+    int rk = 0;
+    for (int j = 0; j < JS; ++j) {
+      const float dj = sm.G[j][j];
+      rk += (dj > di) || (dj == di && j < tid);
+    }
+    sm.rank[tid] = rk;
+    if (rk != tid) sm.nonident = 1;
+  }
+  __syncthreads();
+  if (tid == 0) M.pair_flag[pair] = sm.nonident;
+  if (sm.nonident) {
+    float* et = M.ET + (int64_t)pair * (JS * JS);
+    for (int e = tid; e < JS * JS; e += J_THREADS) {
+      const int c = e / JS, i = e % JS;       // eigenvector c, component i
+      et[sm.rank[c] * JS + i] = (float)sm.E[i][c];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// update: Z_pair[:, cols] <- ET (64x64) * Z_pair[:, cols], in place.
+// grid (ldz/128, npairs, nmat); 256 threads, 4 rows x 8 cols per thread.
+// ---------------------------------------------------------------------------
+constexpr int UP_TN = 128;
+
+__global__ void __launch_bounds__(J_THREADS)
+svd_update_kernel(SvdGroup g, int round) {
+  const SvdMat& M = g.mat[blockIdx.z];
+  if (M.stats[0]) return;
+  const int pair = blockIdx.y;
+  if (!M.pair_flag[pair]) return;
+  __shared__ __align__(16) float Est[JS][JS];   // Est[k][row] = ET[row][k]
+  __shared__ __align__(16) float Zs[JS][UP_TN];
+  int I, J;
+  rr_pair(g.p, round, pair, I, J);
+  const int tid = threadIdx.x;
+  const int col0 = blockIdx.x * UP_TN;
+  const float* et = M.ET + (int64_t)pair * (JS * JS);
+  for (int e = tid; e < JS * JS; e += J_THREADS) Est[e % JS][e / JS] = et[e];
+  // 64 rows x 128 cols as float4: 2048 vectors
+#pragma unroll
+  for (int it = 0; it < (JS * UP_TN / 4) / J_THREADS; ++it) {
+    const int e = tid + it * J_THREADS;
+    const int rr = e >> 5, v = e & 31;
+    const float4 x = *reinterpret_cast<const float4*>(pair_row(M.Z, g.ldz, I, J, rr) + col0 + v * 4);
+    *reinterpret_cast<float4*>(&Zs[rr][v * 4]) = x;
+  }
+  __syncthreads();
+  const int tx = tid & 15, ty = tid >> 4;  // rows ty*4.., cols tx*4.. and 64+tx*4..
+  float acc[4][8] = {};
+#pragma unroll 8
+  for (int k = 0; k < JS; ++k) {
+    const float4 b0 = *reinterpret_cast<const float4*>(&Zs[k][tx * 4]);
+    const float4 b1 = *reinterpret_cast<const float4*>(&Zs[k][64 + tx * 4]);
+    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const float4 a4 = *reinterpret_cast<const float4*>(&Est[k][ty * 4]);
+    const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float* dst = const_cast<float*>(pair_row(M.Z, g.ldz, I, J, ty * 4 + i)) + col0;
+    *reinterpret_cast<float4*>(dst + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    *reinterpret_cast<float4*>(dst + 64 + tx * 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+  }
+}
+
+// one thread per matrix: close the sweep
+__global__ void svd_sweep_end_kernel(SvdGroup g, int sweep, float tol) {
+  const int m = threadIdx.x;
+  if (m >= g.nmat) return;
+  uint32_t* st = g.mat[m].stats;
+  if (st[0]) return;
+  const float off = __uint_as_float(st[8 + sweep]);
+  st[1] = sweep + 1;
+  st[2] = st[8 + sweep];
+  if (off < tol) st[0] = 1;
+}
+
+// ---------------------------------------------------------------------------
+// finalize: sigma_i = |Y_i| (fp64 accumulate), then emit sorted factors
+// ---------------------------------------------------------------------------
+__global__ void svd_norms_kernel(const float* __restrict__ Z, int ldz, int rp, int Lp, float* __restrict__ sigma) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rp) return;
+  const float* y = Z + (int64_t)row * ldz;
+  double acc = 0.0;
+  for (int j = (threadIdx.x & 31) * 4; j < Lp; j += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(y + j);
+    acc += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sigma[row] = (float)sqrt(acc);
+}
+
+// out[i][j] = src[perm[i]][col0 + j] * (normalize ? 1/sigma[perm[i]] : 1),  i < r, j < ncols
+__global__ void svd_emit_rows_kernel(const float* __restrict__ Z, int ldz, int col0, const int64_t* __restrict__ perm,
+                                     const float* __restrict__ sigma, int normalize, int r, int ncols,
+                                     float* __restrict__ out, int64_t ldo, float* __restrict__ S_out) {
+  const int i = blockIdx.x;
+  const int src = (int)perm[i];
+  const float sg = sigma[src];
+  const float scale = normalize ? (sg > 0.f ? 1.f / sg : 0.f) : 1.f;
+  if (S_out && threadIdx.x == 0) S_out[i] = sg;
+  const float* z = Z + (int64_t)src * ldz + col0;
+  for (int j = threadIdx.x; j < ncols; j += blockDim.x) out[(int64_t)i * ldo + j] = z[j] * scale;
+}
+
+// out[a][i] = src[perm[i]][col0 + a] * scale_i,  a < nrows_out, i < r   (tiled transpose)
+__global__ void svd_emit_cols_kernel(const float* __restrict__ Z, int ldz, int col0, const int64_t* __restrict__ perm,
+                                     const float* __restrict__ sigma, int normalize, int r, int nrows_out,
+                                     float* __restrict__ out, int64_t ldo) {
+  __shared__ float tile[32][33];
+  const int i0 = blockIdx.x * 32, a0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int dy = ty; dy < 32; dy += 8) {
+    const int i = i0 + dy, a = a0 + tx;
+    float v = 0.f;
+    if (i < r && a < nrows_out) {
+      const int src = (int)perm[i];
+      const float sg = sigma[src];
+      const float scale = normalize ? (sg > 0.f ? 1.f / sg : 0.f) : 1.f;
+      v = Z[(int64_t)src * ldz + col0 + a] * scale;
+    }
+    tile[dy][tx] = v;
+  }
+  __syncthreads();
+  for (int dy = ty; dy < 32; dy += 8) {
+    const int a = a0 + dy, i = i0 + tx;
+    if (a < nrows_out && i < r) out[(int64_t)a * ldo + i] = tile[tx][dy];
+  }
+}
+
+__global__ void svd_info_kernel(const uint32_t* __restrict__ stats, int32_t* __restrict__ info) {
+  info[0] = (int32_t)stats[1];
+  info[1] = (int32_t)stats[0];
+  info[2] = (int32_t)stats[2];
+  info[3] = 0;
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+struct SvdPlan {
+  int64_t m, n;        // A is m x n
+  int trans;           // 1 when m > n (work on A^T)
+  int r, L, rp, Lp, ldz, p, npairs, nsplit;
+  size_t off_Z, off_G, off_ET, off_flag, off_stats, off_sigma, off_perm, bytes;
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static SvdPlan make_plan(int64_t m, int64_t n) {
+  SvdPlan P{};
+  P.m = m; P.n = n;
+  P.trans = (m > n);
+  P.r = (int)(P.trans ? n : m);
+  P.L = (int)(P.trans ? m : n);
+  P.rp = (int)round_up(P.r, JS);
+  P.Lp = (int)round_up(P.L, UP_TN);
+  P.ldz = P.Lp + (int)round_up(P.rp, UP_TN);
+  P.p = P.rp / JB;
+  P.npairs = P.p / 2;
+  const int chunks = P.Lp / 32;
+  int want = (2 * 148 + P.npairs - 1) / P.npairs;
+  if (want < 1) want = 1;
+  if (want > chunks / 4) want = chunks / 4 > 0 ? chunks / 4 : 1;
+  if (want > 32) want = 32;
+  P.nsplit = want;
+  size_t o = 0;
+  P.off_Z = o;     o = align_up(o + (size_t)P.rp * P.ldz * 4, 256);
+  P.off_G = o;     o = align_up(o + (size_t)P.npairs * P.nsplit * JS * JS * 4, 256);
+  P.off_ET = o;    o = align_up(o + (size_t)P.npairs * JS * JS * 4, 256);
+  P.off_flag = o;  o = align_up(o + (size_t)P.npairs * 4, 256);
+  P.off_stats = o; o = align_up(o + (size_t)J_STATS * 4, 256);
+  P.off_sigma = o; o = align_up(o + (size_t)P.rp * 4, 256);
+  P.off_perm = o;  o = align_up(o + (size_t)P.rp * 8, 256);
+  P.bytes = o;
+  return P;
+}
+
+}  // namespace grasp
+
+using namespace grasp;
+
+extern "C" size_t grasp_svd_workspace_bytes(int batch, const int64_t* m, const int64_t* n) {
+  if (batch <= 0 || !m || !n) return 0;
+  size_t total = 0;
+  for (int i = 0; i < batch; ++i) {
+    if (m[i] <= 0 || n[i] <= 0) return 0;
+    total += make_plan(m[i], n[i]).bytes;
+  }
+  return total;
+}
+
+extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t* m, const int64_t* n,
+                                 const int64_t* lda, float* const* U, float* const* S, float* const* Vh,
+                                 int32_t* info, int prec, int max_sweeps, void* ws, size_t ws_bytes,
+                                 void* stream) {
+  if (batch < 0) return bad_arg("svd: batch");
+  if (batch == 0) return 0;
+  if (!A || !m || !n || !lda || !U || !S || !Vh || !ws) return bad_arg("svd: null");
+  if (prec != GRASP_PREC_SIMT && prec != GRASP_PREC_BF16X3 && prec != GRASP_PREC_BF16X6)
+    return bad_arg("svd: prec");
+  if (max_sweeps <= 0) max_sweeps = 24;
+  if (max_sweeps > J_STATS - 8) max_sweeps = J_STATS - 8;
+  for (int i = 0; i < batch; ++i) {
+    if (!A[i] || !U[i] || !S[i] || !Vh[i]) return bad_arg("svd: null matrix pointer");
+    if (m[i] <= 0 || n[i] <= 0 || lda[i] < n[i]) return bad_arg("svd: m/n/lda");
+    if (m[i] > 65536 || n[i] > 65536) return bad_arg("svd: dimension > 65536");
+    if ((m[i] < n[i] ? m[i] : n[i]) > 16384) return bad_arg("svd: min(m,n) > 16384 unsupported");
+  }
+  if (ws_bytes < grasp_svd_workspace_bytes(batch, m, n)) return bad_arg("svd: workspace too small");
+  if (reinterpret_cast<uintptr_t>(ws) & 255) return bad_arg("svd: workspace must be 256-byte aligned");
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    int rc = check_cuda(cudaFuncSetAttribute(svd_evd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(EvdSmem)), "svd_evd attr");
+    if (rc) return rc;
+    attr_set = true;
+  }
+  const float tol = 5e-7f;
+  const int inner_cap = 3;
+  cudaStream_t st = (cudaStream_t)stream;
+
+  // plans + workspace carving
+  SvdPlan* plans = new SvdPlan[batch];
+  unsigned char** base = new unsigned char*[batch];
+  bool* done = new bool[batch];
+  {
+    unsigned char* cur = static_cast<unsigned char*>(ws);
+    for (int i = 0; i < batch; ++i) {
+      plans[i] = make_plan(m[i], n[i]);
+      base[i] = cur;
+      cur += plans[i].bytes;
+      done[i] = false;
+    }
+  }
+  int rc = 0;
+  for (int i0 = 0; i0 < batch && !rc; ++i0) {
+    if (done[i0]) continue;
+    // group up to J_MAXMAT matrices with the same working shape
+    SvdGroup g{};
+    int members[J_MAXMAT];
+    const SvdPlan& P = plans[i0];
+    for (int i = i0; i < batch && g.nmat < J_MAXMAT; ++i) {
+      if (done[i]) continue;
+      if (plans[i].rp == P.rp && plans[i].Lp == P.Lp) {
+        members[g.nmat] = i;
+        SvdMat& M = g.mat[g.nmat++];
+        M.Z = reinterpret_cast<float*>(base[i] + plans[i].off_Z);
+        M.Gpart = reinterpret_cast<float*>(base[i] + plans[i].off_G);
+        M.ET = reinterpret_cast<float*>(base[i] + plans[i].off_ET);
+        M.pair_flag = reinterpret_cast<int*>(base[i] + plans[i].off_flag);
+        M.stats = reinterpret_cast<uint32_t*>(base[i] + plans[i].off_stats);
+        done[i] = true;
+      }
+    }
+    g.rp = P.rp; g.Lp = P.Lp; g.ldz = P.ldz; g.p = P.p; g.npairs = P.npairs; g.nsplit = P.nsplit;
+
+    for (int j = 0; j < g.nmat && !rc; ++j) {
+      const int i = members[j];
+      const SvdPlan& Q = plans[i];
+      rc = check_cuda(cudaMemsetAsync(g.mat[j].stats, 0, J_STATS * 4, st), "svd memset");
+      if (rc) break;
+      dim3 grid((unsigned)(Q.ldz / 32), (unsigned)(Q.rp / 32));
+      GRASP_LAUNCH(svd_init_kernel, grid, dim3(32, 8), 0, st, A[i], lda[i], Q.r, Q.L, Q.trans,
+                   g.mat[j].Z, Q.rp, Q.Lp, Q.ldz);
+    }
+    if (rc) break;
+    rc = check_cuda(cudaGetLastError(), "svd_init_kernel");
+    if (rc) break;
+
+    if (g.p >= 2) {
+      for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+        for (int round = 0; round < g.p - 1; ++round) {
+          GRASP_LAUNCH(svd_gram_kernel, dim3(g.nsplit, g.npairs, g.nmat), dim3(J_THREADS), 0, st, g, round);
+          GRASP_LAUNCH(svd_evd_kernel, dim3(g.npairs, g.nmat), dim3(J_THREADS), sizeof(EvdSmem), st, g, round,
+                       sweep, tol, inner_cap);
+          GRASP_LAUNCH(svd_update_kernel, dim3(g.ldz / UP_TN, g.npairs, g.nmat), dim3(J_THREADS), 0, st, g, round);
+        }
+        GRASP_LAUNCH(svd_sweep_end_kernel, dim3(1), dim3(32), 0, st, g, sweep, tol);
+      }
+      rc = check_cuda(cudaGetLastError(), "svd sweep kernels");
+      if (rc) break;
+    }
+
+    // finalize each member
+    for (int j = 0; j < g.nmat && !rc; ++j) {
+      const int i = members[j];
+      const SvdPlan& Q = plans[i];
+      float* sigma = reinterpret_cast<float*>(base[i] + Q.off_sigma);
+      int64_t* perm = reinterpret_cast<int64_t*>(base[i] + Q.off_perm);
+      GRASP_LAUNCH(svd_norms_kernel, dim3((Q.rp + 7) / 8), dim3(256), 0, st, g.mat[j].Z, Q.ldz, Q.rp, Q.Lp, sigma);
+      const float* sc = sigma;
+      int64_t rr = Q.rp, kk = Q.rp;
+      rc = grasp_topk_batched(1, &sc, &rr, &kk, &perm, stream);
+      if (rc) break;
+      if (!Q.trans) {
+        // Vh = normalised rows of Y, U = QT^T
+        GRASP_LAUNCH(svd_emit_rows_kernel, dim3(Q.r), dim3(256), 0, st, g.mat[j].Z, Q.ldz, 0, perm, sigma, 1, Q.r,
+                     (int)Q.n, Vh[i], (int64_t)Q.n, S[i]);
+        GRASP_LAUNCH(svd_emit_cols_kernel, dim3((Q.r + 31) / 32, (unsigned)((Q.m + 31) / 32)), dim3(32, 8), 0, st,
+                     g.mat[j].Z, Q.ldz, Q.Lp, perm, sigma, 0, Q.r, (int)Q.m, U[i], (int64_t)Q.r);
+      } else {
+        // U = (normalised rows of Y)^T, Vh = QT
+        GRASP_LAUNCH(svd_emit_cols_kernel, dim3((Q.r + 31) / 32, (unsigned)((Q.m + 31) / 32)), dim3(32, 8), 0, st,
+                     g.mat[j].Z, Q.ldz, 0, perm, sigma, 1, Q.r, (int)Q.m, U[i], (int64_t)Q.r);
+        GRASP_LAUNCH(svd_emit_rows_kernel, dim3(Q.r), dim3(256), 0, st, g.mat[j].Z, Q.ldz, Q.Lp, perm, sigma, 0, Q.r,
+                     (int)Q.n, Vh[i], (int64_t)Q.n, S[i]);
+      }
+      if (info) GRASP_LAUNCH(svd_info_kernel, dim3(1), dim3(1), 0, st, g.mat[j].stats, info + 4 * i);
+      rc = check_cuda(cudaGetLastError(), "svd finalize");
+    }
+  }
+  delete[] plans;
+  delete[] base;
+  delete[] done;
+  return rc;
+}

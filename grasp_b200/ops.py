@@ -1,0 +1,320 @@
+"""torch-tensor wrappers over the C ABI (include/grasp_b200.h).
+
+PyTorch is only the memory/stream provider here: every function hands raw device
+pointers and the current CUDA stream to libgrasp_b200.so.  Nothing falls back to
+torch.linalg / torch.topk / CPU -- a CPU tensor or a missing library raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (DTYPE_BF16, DTYPE_F16, DTYPE_F32, METRIC_GRADIENT, METRIC_TAYLOR, PREC_BF16X3, PREC_BF16X6,
+                   PREC_SIMT, GraspLibraryError, check)
+
+# arithmetic of the GEMM-shaped stages; see include/grasp_b200.h
+_DEFAULT_PREC = PREC_SIMT
+
+
+def set_default_precision(prec: int) -> None:
+    global _DEFAULT_PREC
+    if prec not in (PREC_SIMT, PREC_BF16X3, PREC_BF16X6):
+        raise ValueError(f"unknown precision {prec}")
+    _DEFAULT_PREC = prec
+
+
+def default_precision() -> int:
+    return _DEFAULT_PREC
+
+
+def _prec(prec: Optional[int]) -> int:
+    return _DEFAULT_PREC if prec is None else prec
+
+
+_DTYPES = {torch.float32: DTYPE_F32, torch.bfloat16: DTYPE_BF16, torch.float16: DTYPE_F16}
+
+
+def _need_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise GraspLibraryError("grasp_b200 ops need CUDA tensors (there is no CPU fallback)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise GraspLibraryError("tensors live on different devices")
+    return dev
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    # torch's caching allocator hands out 512-byte aligned blocks
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def launch_count() -> int:
+    return int(_lib.load().grasp_launch_count())
+
+
+# --------------------------------------------------------------------------- BI
+def bi_accumulate(h_in: torch.Tensor, h_out: torch.Tensor, acc: Optional[torch.Tensor] = None,
+                  angular: bool = False, per_row: bool = False) -> Optional[torch.Tensor]:
+    """acc[0] += mean_t BI(h_in[t], h_out[t]); optionally returns the per-token BI (fp32 [rows])."""
+    lib = _lib.load()
+    dev = _need_cuda(h_in, h_out, acc)
+    if h_in.shape != h_out.shape or h_in.dtype != h_out.dtype:
+        raise ValueError("hidden states must have identical shape and dtype")
+    if h_in.dtype not in _DTYPES:
+        raise TypeError(f"unsupported hidden-state dtype {h_in.dtype}")
+    d = h_in.shape[-1]
+    x = h_in.reshape(-1, d).contiguous()
+    y = h_out.reshape(-1, d).contiguous()
+    rows = x.shape[0]
+    out = torch.empty(rows, dtype=torch.float32, device=dev) if per_row else None
+    if acc is not None and (acc.dtype != torch.float64 or acc.numel() < 1):
+        raise TypeError("acc must be a float64 device tensor")
+    if acc is None and out is None:
+        raise ValueError("nothing to compute: pass acc and/or per_row=True")
+    with torch.cuda.device(dev):
+        check(lib.grasp_bi_accumulate(x.data_ptr(), y.data_ptr(), rows, d, d, _DTYPES[x.dtype], int(bool(angular)),
+                                      acc.data_ptr() if acc is not None else None,
+                                      out.data_ptr() if out is not None else None, _stream()), "grasp_bi_accumulate")
+    return out
+
+
+def bi_chain(hiddens: Sequence[torch.Tensor], acc: torch.Tensor) -> None:
+    """acc[i] += mean_t BI(hiddens[i], hiddens[i+1]) for the L+1 hidden states of one forward pass."""
+    lib = _lib.load()
+    dev = _need_cuda(*hiddens, acc)
+    n = len(hiddens)
+    if n < 2:
+        raise ValueError("need at least two hidden states")
+    d = hiddens[0].shape[-1]
+    hs = []
+    for h in hiddens:
+        if h.shape != hiddens[0].shape or h.dtype != hiddens[0].dtype:
+            raise ValueError("hidden states must share shape and dtype")
+        hs.append(h.reshape(-1, d).contiguous())
+    if hs[0].dtype not in _DTYPES:
+        raise TypeError(f"unsupported hidden-state dtype {hs[0].dtype}")
+    if acc.dtype != torch.float64 or acc.numel() < n - 1 or not acc.is_contiguous():
+        raise TypeError("acc must be a contiguous float64 device tensor with >= len(hiddens)-1 entries")
+    rows = hs[0].shape[0]
+    ptrs = _lib.ptr_array([h.data_ptr() for h in hs])
+    with torch.cuda.device(dev):
+        check(lib.grasp_bi_chain(ptrs, n, rows, d, d, _DTYPES[hs[0].dtype], acc.data_ptr(), _stream()),
+              "grasp_bi_chain")
+
+
+# -------------------------------------------------------------------------- SVD
+def svd_batched(mats: Sequence[torch.Tensor], prec: Optional[int] = None, max_sweeps: int = 0,
+                return_info: bool = False):
+    """Thin SVD of each fp32 matrix: returns [(U [m,r], S [r] descending, Vh [r,n])]."""
+    lib = _lib.load()
+    dev = _need_cuda(*mats)
+    if len(mats) == 0:
+        return ([], None) if return_info else []
+    As = []
+    for w in mats:
+        if w.dim() != 2:
+            raise ValueError("svd expects 2-D matrices")
+        As.append(_f32c(w, "matrix"))
+    m = [a.shape[0] for a in As]
+    n = [a.shape[1] for a in As]
+    r = [min(a.shape) for a in As]
+    Us = [torch.empty(mi, ri, dtype=torch.float32, device=dev) for mi, ri in zip(m, r)]
+    Ss = [torch.empty(ri, dtype=torch.float32, device=dev) for ri in r]
+    Vs = [torch.empty(ri, ni, dtype=torch.float32, device=dev) for ri, ni in zip(r, n)]
+    info = torch.zeros(4 * len(As), dtype=torch.int32, device=dev)
+    m_a, n_a = _lib.i64_array(m), _lib.i64_array(n)
+    nbytes = lib.grasp_svd_workspace_bytes(len(As), m_a, n_a)
+    if nbytes == 0:
+        raise GraspLibraryError("grasp_svd_workspace_bytes rejected the shapes")
+    ws = _workspace(nbytes, dev)
+    with torch.cuda.device(dev):
+        check(lib.grasp_svd_batched(len(As), _lib.ptr_array([a.data_ptr() for a in As]), m_a, n_a, _lib.i64_array(n),
+                                    _lib.ptr_array([u.data_ptr() for u in Us]),
+                                    _lib.ptr_array([s.data_ptr() for s in Ss]),
+                                    _lib.ptr_array([v.data_ptr() for v in Vs]), info.data_ptr(), _prec(prec),
+                                    int(max_sweeps), ws.data_ptr(), ws.numel(), _stream()), "grasp_svd_batched")
+    # keep the workspace alive until the stream has consumed it
+    ws.record_stream(torch.cuda.current_stream())
+    out = list(zip(Us, Ss, Vs))
+    return (out, info.view(-1, 4)) if return_info else out
+
+
+def svd(w: torch.Tensor, prec: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Drop-in for torch.linalg.svd(w, full_matrices=False) on a CUDA fp32 matrix."""
+    return svd_batched([w], prec=prec)[0]
+
+
+# ---------------------------------------------------------------------- scoring
+def _metric(metric) -> int:
+    if metric in (METRIC_GRADIENT, "gradient"):
+        return METRIC_GRADIENT
+    if metric in (METRIC_TAYLOR, "taylor"):
+        return METRIC_TAYLOR
+    raise RuntimeError(f"{metric} not support")
+
+
+def sigma_score(U: torch.Tensor, G: torch.Tensor, Vh: torch.Tensor, S: Optional[torch.Tensor], metric="taylor",
+                dsigma: Optional[torch.Tensor] = None, want_score: bool = True, prec: Optional[int] = None):
+    """dsigma[i] (+)= u_i^T G v_i ; score = |dsigma| (gradient) or |dsigma*S| (taylor).
+
+    Pass an existing `dsigma` to accumulate into it.  Returns (dsigma, score or None)."""
+    lib = _lib.load()
+    dev = _need_cuda(U, G, Vh, S, dsigma)
+    U, G, Vh = _f32c(U, "U"), _f32c(G, "G"), _f32c(Vh, "Vh")
+    out, r = U.shape
+    in_ = Vh.shape[1]
+    if G.shape != (out, in_) or Vh.shape[0] != r:
+        raise ValueError(f"shape mismatch: U {tuple(U.shape)} G {tuple(G.shape)} Vh {tuple(Vh.shape)}")
+    if S is not None:
+        S = _f32c(S, "S")
+    accumulate = dsigma is not None
+    if dsigma is None:
+        dsigma = torch.empty(r, dtype=torch.float32, device=dev)
+    elif dsigma.dtype != torch.float32 or not dsigma.is_contiguous() or dsigma.numel() != r:
+        raise TypeError("dsigma must be a contiguous float32 tensor of length r")
+    score = torch.empty(r, dtype=torch.float32, device=dev) if want_score else None
+    p = _prec(prec)
+    ws = _workspace(lib.grasp_sigma_score_workspace_bytes(out, in_, r, p), dev)
+    with torch.cuda.device(dev):
+        check(lib.grasp_sigma_score(U.data_ptr(), G.data_ptr(), Vh.data_ptr(), S.data_ptr() if S is not None else None,
+                                    out, in_, r, _metric(metric), int(accumulate), dsigma.data_ptr(),
+                                    score.data_ptr() if score is not None else None, p, ws.data_ptr(), ws.numel(),
+                                    _stream()), "grasp_sigma_score")
+    ws.record_stream(torch.cuda.current_stream())
+    return dsigma, score
+
+
+def score_from_grad(dsigma: torch.Tensor, S: Optional[torch.Tensor], metric="taylor") -> torch.Tensor:
+    lib = _lib.load()
+    dev = _need_cuda(dsigma, S)
+    g = _f32c(dsigma, "dsigma")
+    s = _f32c(S, "S") if S is not None else None
+    score = torch.empty_like(g)
+    with torch.cuda.device(dev):
+        check(lib.grasp_score_from_grad(g.data_ptr(), s.data_ptr() if s is not None else None, g.numel(),
+                                        _metric(metric), score.data_ptr(), _stream()), "grasp_score_from_grad")
+    return score
+
+
+def topk_batched(scores: Sequence[torch.Tensor], ks: Sequence[int]) -> List[torch.Tensor]:
+    """Indices of the k largest scores of each vector, sorted by score descending (int64)."""
+    lib = _lib.load()
+    dev = _need_cuda(*scores)
+    if len(scores) != len(ks):
+        raise ValueError("scores and ks differ in length")
+    if not scores:
+        return []
+    sc = [_f32c(s.reshape(-1), "score") for s in scores]
+    outs = [torch.empty(int(k), dtype=torch.int64, device=dev) for k in ks]
+    with torch.cuda.device(dev):
+        check(lib.grasp_topk_batched(len(sc), _lib.ptr_array([s.data_ptr() for s in sc]),
+                                     _lib.i64_array([s.numel() for s in sc]), _lib.i64_array(ks),
+                                     _lib.ptr_array([o.data_ptr() for o in outs]), _stream()), "grasp_topk_batched")
+    return outs
+
+
+def topk(score: torch.Tensor, k: int) -> torch.Tensor:
+    return topk_batched([score], [k])[0]
+
+
+def adaptive_rank(score: torch.Tensor, target_ratio: float) -> torch.Tensor:
+    """tools/utils_func.py:45-57 on the device; returns the kept indices (descending score)."""
+    lib = _lib.load()
+    dev = _need_cuda(score)
+    s = _f32c(score.reshape(-1), "score")
+    idx = torch.empty(s.numel(), dtype=torch.int64, device=dev)
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.grasp_adaptive_rank(s.data_ptr(), s.numel(), float(target_ratio), idx.data_ptr(), count.data_ptr(),
+                                      _stream()), "grasp_adaptive_rank")
+    return idx[: int(count.item())]
+
+
+# ---------------------------------------------------------------------- compile
+def lowrank_rebuild(U: torch.Tensor, S: torch.Tensor, Vh: torch.Tensor, idx: torch.Tensor,
+                    out_dtype: torch.dtype = torch.float32, prec: Optional[int] = None) -> torch.Tensor:
+    """W = U[:, idx] diag(S[idx]) Vh[idx, :]."""
+    lib = _lib.load()
+    dev = _need_cuda(U, S, Vh, idx)
+    U, S, Vh = _f32c(U, "U"), _f32c(S, "S"), _f32c(Vh, "Vh")
+    if idx.dtype != torch.int64:
+        raise TypeError("idx must be int64")
+    idx = idx.contiguous()
+    out, r = U.shape
+    in_ = Vh.shape[1]
+    k = idx.numel()
+    if out_dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError("out_dtype must be float32 or bfloat16")
+    W = torch.empty(out, in_, dtype=out_dtype, device=dev)
+    p = _prec(prec)
+    ws = _workspace(lib.grasp_lowrank_rebuild_workspace_bytes(out, in_, k, p), dev)
+    with torch.cuda.device(dev):
+        check(lib.grasp_lowrank_rebuild(U.data_ptr(), S.data_ptr(), Vh.data_ptr(), idx.data_ptr(), k, out, in_, r,
+                                        _DTYPES[out_dtype], W.data_ptr(), p, ws.data_ptr(), ws.numel(), _stream()),
+              "grasp_lowrank_rebuild")
+    ws.record_stream(torch.cuda.current_stream())
+    return W
+
+
+def factor_pack(U: torch.Tensor, S: torch.Tensor, Vh: torch.Tensor, idx: torch.Tensor):
+    """(in_w [k,in] = Vh[idx]*sqrt(S[idx])[:,None], out_w [out,k] = U[:,idx]*sqrt(S[idx]))."""
+    lib = _lib.load()
+    dev = _need_cuda(U, S, Vh, idx)
+    U, S, Vh = _f32c(U, "U"), _f32c(S, "S"), _f32c(Vh, "Vh")
+    if idx.dtype != torch.int64:
+        raise TypeError("idx must be int64")
+    idx = idx.contiguous()
+    out, r = U.shape
+    in_ = Vh.shape[1]
+    k = idx.numel()
+    in_w = torch.empty(k, in_, dtype=torch.float32, device=dev)
+    out_w = torch.empty(out, k, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.grasp_factor_pack(U.data_ptr(), S.data_ptr(), Vh.data_ptr(), idx.data_ptr(), k, out, in_, r,
+                                    in_w.data_ptr(), out_w.data_ptr(), _stream()), "grasp_factor_pack")
+    return in_w, out_w
+
+
+# ------------------------------------------------------------------------- GEMM
+def gemm(A: torch.Tensor, B: torch.Tensor, ta: bool = False, tb: bool = False, alpha: float = 1.0,
+         beta: float = 0.0, C_out: Optional[torch.Tensor] = None, prec: Optional[int] = None) -> torch.Tensor:
+    """C = alpha * op(A) op(B) + beta * C (fp32, row-major)."""
+    lib = _lib.load()
+    dev = _need_cuda(A, B, C_out)
+    A, B = _f32c(A, "A"), _f32c(B, "B")
+    M, K = (A.shape[1], A.shape[0]) if ta else (A.shape[0], A.shape[1])
+    K2, N = (B.shape[1], B.shape[0]) if tb else (B.shape[0], B.shape[1])
+    if K != K2:
+        raise ValueError("inner dimensions differ")
+    if C_out is None:
+        if beta != 0.0:
+            raise ValueError("beta != 0 needs C_out")
+        C_out = torch.empty(M, N, dtype=torch.float32, device=dev)
+    elif C_out.dtype != torch.float32 or not C_out.is_contiguous() or C_out.shape != (M, N):
+        raise TypeError("C_out must be a contiguous float32 [M,N] tensor")
+    p = _prec(prec)
+    ws = _workspace(lib.grasp_gemm_workspace_bytes(M, N, K, p), dev)
+    with torch.cuda.device(dev):
+        check(lib.grasp_gemm_f32(int(ta), int(tb), M, N, K, float(alpha), A.data_ptr(), A.shape[1], B.data_ptr(),
+                                 B.shape[1], float(beta), C_out.data_ptr(), N, p, ws.data_ptr(), ws.numel(),
+                                 _stream()), "grasp_gemm_f32")
+    ws.record_stream(torch.cuda.current_stream())
+    return C_out

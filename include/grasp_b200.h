@@ -1,0 +1,156 @@
+/*
+ * grasp_b200.h -- C ABI of the B200-native GRASP compression hot path.
+ *
+ * The reference (compressionOrg/GRASP) is pure Python/PyTorch and has no FFI of
+ * its own; each entry point below replaces one torch library call site of the
+ * reference hot path (file:line given per function, paths relative to the
+ * reference root).  Contract shared by every function unless stated otherwise:
+ *
+ *   - all pointers are DEVICE pointers owned by the caller (inputs, outputs and
+ *     workspace); matrices are row-major with explicit leading dimensions in
+ *     ELEMENTS; nothing is allocated or freed inside the library;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); the call
+ *     never synchronises the device and is re-entrant per stream;
+ *   - return value: 0 = ok, <0 = bad argument (nothing was enqueued),
+ *     >0 = CUDA error code; text via grasp_last_error() (thread-local);
+ *   - there is no CPU fallback: without an sm_100 device the calls return a
+ *     CUDA error.
+ */
+#ifndef GRASP_B200_H
+#define GRASP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRASP_ABI_VERSION 1
+
+/* element types of hidden states / outputs */
+#define GRASP_DTYPE_F32  0
+#define GRASP_DTYPE_BF16 1
+#define GRASP_DTYPE_F16  2
+
+/* importance metric, reference modeling_grasp.py:392-397 */
+#define GRASP_METRIC_GRADIENT 0
+#define GRASP_METRIC_TAYLOR   1
+
+/* GEMM arithmetic used by the tensor-core paths: fp32 operands are split into
+ * bf16 planes (hi, mid, lo) and multiplied on tcgen05 with fp32 accumulation.
+ *   GRASP_PREC_SIMT  : plain fp32 FMA on CUDA cores (validation path)
+ *   GRASP_PREC_BF16X3: 2 planes, 3 MMAs  (rel. err ~4e-6)
+ *   GRASP_PREC_BF16X6: 3 planes, 6 MMAs  (rel. err ~1e-7, fp32-class)          */
+#define GRASP_PREC_SIMT   0
+#define GRASP_PREC_BF16X3 3
+#define GRASP_PREC_BF16X6 6
+
+int         grasp_abi_version(void);
+const char* grasp_last_error(void);
+/* number of kernels this library has launched in the calling process (all
+ * streams); bench.py reports the difference over its timed region. */
+uint64_t    grasp_launch_count(void);
+
+/* ---------------------------------------------------------------------------
+ * (a1) block influence of one layer pair.  Replaces tools/utils_func.py:3-25
+ * (block_influence) as called from modeling_grasp.py:163-167: per token row t
+ *   sim_t = <x_t,y_t>/(|x_t||y_t|), NaN -> 0.5, bi_t = 1-sim_t
+ *   (angular != 0: bi_t = arccos(sim_t)/pi)
+ * and *acc += mean_t(bi_t)  (acc is a device double, so the per-batch sums the
+ * reference keeps in Python floats stay on the device).  per_row (nullable)
+ * receives bi_t as fp32 [rows].  ld = row stride in elements.
+ * ------------------------------------------------------------------------- */
+int grasp_bi_accumulate(const void* h_in, const void* h_out, int64_t rows, int64_t d,
+                        int64_t ld, int dtype, int angular,
+                        double* acc, float* per_row, void* stream);
+
+/* (a2) the whole chain of one forward pass: hiddens[0..n_states) are the
+ * L+1 hidden states of modeling_grasp.py:180-183 (HOST array of device
+ * pointers, each [rows, d] with row stride ld); acc[i] += mean_t BI(h[i],h[i+1])
+ * for i in [0, n_states-1).  Every hidden state is read from HBM exactly once.
+ * n_states <= 130. */
+int grasp_bi_chain(const void* const* hiddens, int n_states, int64_t rows, int64_t d,
+                   int64_t ld, int dtype, double* acc, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * (a3) thin SVD, replaces torch.linalg.svd(w, full_matrices=False) at
+ * modeling_grasp.py:231.  A[i] is m[i] x n[i] fp32 (lda[i]); outputs
+ * U[i] [m, r] (ld r), S[i] [r] descending, Vh[i] [r, n] (ld n), r = min(m,n).
+ * info (device int32 [4*batch]): {sweeps used, converged(0/1),
+ * float bits of the last sweep's max relative off-diagonal, reserved}.
+ * prec: GRASP_PREC_*; max_sweeps <= 0 selects the default (24).
+ * All shape arrays are HOST arrays; A/U/S/Vh are HOST arrays of device ptrs.
+ * ------------------------------------------------------------------------- */
+size_t grasp_svd_workspace_bytes(int batch, const int64_t* m, const int64_t* n);
+int    grasp_svd_batched(int batch, const float* const* A, const int64_t* m, const int64_t* n,
+                         const int64_t* lda, float* const* U, float* const* S, float* const* Vh,
+                         int32_t* info, int prec, int max_sweeps,
+                         void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * (a5/a6) singular-value gradient and importance.  Replaces the autograd path
+ * through GRASPLayer (modeling_grasp.py:75-79, :354-363) by the identity
+ * dL/dS_i = u_i^T G v_i with G = dL/dW [out,in] accumulated over the
+ * calibration samples, and the score of modeling_grasp.py:392-395:
+ *   dsigma[i] (+)= sum_{a,b} U[a,i] G[a,b] Vh[i,b]
+ *   score[i]   = |dsigma[i]| (gradient) or |dsigma[i]*S[i]| (taylor)
+ * U [out,r], G [out,in], Vh [r,in], S [r], all fp32 contiguous.
+ * accumulate != 0 adds into dsigma (multi-call / multi-rank partial sums);
+ * score may be NULL (e.g. before the all-reduce of dsigma).
+ * ------------------------------------------------------------------------- */
+size_t grasp_sigma_score_workspace_bytes(int64_t out, int64_t in, int64_t r, int prec);
+int    grasp_sigma_score(const float* U, const float* G, const float* Vh, const float* S,
+                         int64_t out, int64_t in, int64_t r, int metric, int accumulate,
+                         float* dsigma, float* score, int prec,
+                         void* ws, size_t ws_bytes, void* stream);
+/* score only (after an all-reduce of dsigma): score[i] = |g[i]| or |g[i]*S[i]| */
+int    grasp_score_from_grad(const float* dsigma, const float* S, int64_t r, int metric,
+                             float* score, void* stream);
+
+/* (a6) per-matrix top-k, replaces torch.topk at modeling_grasp.py:404.
+ * idx[i][0..k[i]) = indices of the k largest scores, sorted by score
+ * descending (ties: lower index first; NaN ranks above +inf like torch).
+ * score/idx are HOST arrays of device pointers, r/k HOST arrays. r <= 65536. */
+int grasp_topk_batched(int batch, const float* const* score, const int64_t* r, const int64_t* k,
+                       int64_t* const* idx, void* stream);
+
+/* (a6, threshold mode) tools/utils_func.py:45-57: sort descending, keep the
+ * shortest prefix whose running sum reaches target_ratio * sum(score).
+ * idx [r] receives the full descending order, *count (device int64) the
+ * prefix length. */
+int grasp_adaptive_rank(const float* score, int64_t r, double target_ratio,
+                        int64_t* idx, int64_t* count, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * (a7) compile.  Replaces modeling_grasp.py:440-442 + :454 (merge) and
+ * :47-48 (SVDLinear "UV" fuse).
+ *   rebuild: W[out,in] = U[:,idx] diag(S[idx]) Vh[idx,:]   (fp32 or bf16 out)
+ *   pack   : in_w [k,in] = Vh[idx,:]*sqrt(S[idx])[:,None],
+ *            out_w[out,k] = U[:,idx]*sqrt(S[idx])[None,:]
+ * ------------------------------------------------------------------------- */
+size_t grasp_lowrank_rebuild_workspace_bytes(int64_t out, int64_t in, int64_t k, int prec);
+int    grasp_lowrank_rebuild(const float* U, const float* S, const float* Vh, const int64_t* idx,
+                             int64_t k, int64_t out, int64_t in, int64_t r,
+                             int out_dtype, void* W, int prec,
+                             void* ws, size_t ws_bytes, void* stream);
+int    grasp_factor_pack(const float* U, const float* S, const float* Vh, const int64_t* idx,
+                         int64_t k, int64_t out, int64_t in, int64_t r,
+                         float* in_w, float* out_w, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * (f1) fp32 GEMM on the same arithmetic the SVD uses (building block, also
+ * used by the calibration engine for G += dY^T X):
+ *   C[M,N] = alpha * op(A) op(B) + beta * C,  op = transpose when ta/tb != 0
+ * A is [M,K] (ta=0) or [K,M] (ta=1); B is [K,N] (tb=0) or [N,K] (tb=1).
+ * ------------------------------------------------------------------------- */
+size_t grasp_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int prec);
+int    grasp_gemm_f32(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha,
+                      const float* A, int64_t lda, const float* B, int64_t ldb,
+                      float beta, float* C, int64_t ldc, int prec,
+                      void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRASP_B200_H */
