@@ -78,6 +78,8 @@ def compress(grasp_model: GRASPModel, calibration_dataloader: DataLoader, layers
             if attn_target_layer_types is not None:
                 names += grasp_model.block_target_names(layer_id, "attention", attn_target_layer_types)
         grasp_model.precompute_svd(names, device=device)
+    # one forward sweep caches the input of every selected layer for all calibration samples
+    grasp_model.prepare_calibration(calibration_dataloader, layers_id, device=device)
 
     blocks = (("mlp", mlp_target_layer_types), ("attention", attn_target_layer_types))
     for layer_id in tqdm(layers_id, desc="GRASP Compressing", total=len(layers_id), leave=True):

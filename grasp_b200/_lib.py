@@ -21,8 +21,9 @@ SIGNATURES = {
     "grasp_last_error": (C.c_char_p, []),
     "grasp_launch_count": (C.c_uint64, []),
     "grasp_bi_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int,
-                                      C.c_void_p, C.c_void_p, C.c_void_p]),
-    "grasp_bi_chain": (C.c_int, [_vpp, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+                                      C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "grasp_bi_chain": (C.c_int, [_vpp, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_double, C.c_void_p,
+                                 C.c_void_p]),
     "grasp_svd_workspace_bytes": (C.c_size_t, [C.c_int, _i64p, _i64p]),
     "grasp_svd_batched": (C.c_int, [C.c_int, _vpp, _i64p, _i64p, _i64p, _vpp, _vpp, _vpp, C.c_void_p, C.c_int,
                                     C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -73,7 +73,7 @@ struct ChainPtrs {
 // one CTA per token row; walks the L+1 hidden states keeping the previous row in registers
 template <typename T>
 __global__ void __launch_bounds__(BI_THREADS)
-bi_chain_kernel(ChainPtrs ptrs, int n_states, int64_t rows, int64_t d, int64_t ld, double* acc) {
+bi_chain_kernel(ChainPtrs ptrs, int n_states, int64_t rows, int64_t d, int64_t ld, double scale, double* acc) {
   __shared__ float red[64];
   using V = Vec16<T>;
   const int64_t row = blockIdx.x;
@@ -102,7 +102,7 @@ bi_chain_kernel(ChainPtrs ptrs, int n_states, int64_t rows, int64_t d, int64_t l
   if (n_states > 1) load_row(1, cur);
   block_sum2(nprev, dummy, red);
 
-  const double inv_rows = 1.0 / (double)rows;
+  const double inv_rows = scale / (double)rows;
   for (int s = 1; s < n_states; ++s) {
     float dot = 0.f, ncur = 0.f;
 #pragma unroll
@@ -129,7 +129,7 @@ bi_chain_kernel(ChainPtrs ptrs, int n_states, int64_t rows, int64_t d, int64_t l
 template <typename T>
 __global__ void __launch_bounds__(BI_THREADS)
 bi_pair_kernel(const T* __restrict__ x, const T* __restrict__ y, int64_t rows, int64_t d, int64_t ld,
-               int angular, double* acc, float* per_row) {
+               int angular, double scale, double* acc, float* per_row) {
   __shared__ float red[64];
   using V = Vec16<T>;
   const int64_t row = blockIdx.x;
@@ -167,15 +167,15 @@ bi_pair_kernel(const T* __restrict__ x, const T* __restrict__ y, int64_t rows, i
   if (threadIdx.x == 0) {
     const float bi = bi_from(dot, nx, ny, angular);
     if (per_row) per_row[row] = bi;
-    if (acc) atomicAdd(acc, (double)bi / (double)rows);
+    if (acc) atomicAdd(acc, (double)bi * scale / (double)rows);
   }
 }
 
 template <typename T>
 static int launch_pair(const void* x, const void* y, int64_t rows, int64_t d, int64_t ld, int angular,
-                       double* acc, float* per_row, void* stream) {
+                       double scale, double* acc, float* per_row, void* stream) {
   GRASP_LAUNCH((bi_pair_kernel<T>), dim3((unsigned)rows), dim3(BI_THREADS), 0, stream,
-               static_cast<const T*>(x), static_cast<const T*>(y), rows, d, ld, angular, acc, per_row);
+               static_cast<const T*>(x), static_cast<const T*>(y), rows, d, ld, angular, scale, acc, per_row);
   GRASP_CHECK_LAST("bi_pair_kernel");
   return 0;
 }
@@ -185,23 +185,23 @@ static int launch_pair(const void* x, const void* y, int64_t rows, int64_t d, in
 using namespace grasp;
 
 extern "C" int grasp_bi_accumulate(const void* h_in, const void* h_out, int64_t rows, int64_t d,
-                                   int64_t ld, int dtype, int angular, double* acc, float* per_row,
-                                   void* stream) {
-  if (!h_in || !h_out) return bad_arg("bi: null hidden state");
+                                   int64_t ld, int dtype, int angular, double scale, double* acc,
+                                   float* per_row, void* stream) {
   if (rows < 0 || d <= 0 || ld < d) return bad_arg("bi: rows/d/ld");
   if (!acc && !per_row) return bad_arg("bi: no output");
   if (rows == 0) return 0;
+  if (!h_in || !h_out) return bad_arg("bi: null hidden state");
   if (rows > 0x7fffffffLL) return bad_arg("bi: rows too large");
   switch (dtype) {
-    case GRASP_DTYPE_F32: return launch_pair<float>(h_in, h_out, rows, d, ld, angular, acc, per_row, stream);
-    case GRASP_DTYPE_BF16: return launch_pair<__nv_bfloat16>(h_in, h_out, rows, d, ld, angular, acc, per_row, stream);
-    case GRASP_DTYPE_F16: return launch_pair<__half>(h_in, h_out, rows, d, ld, angular, acc, per_row, stream);
+    case GRASP_DTYPE_F32: return launch_pair<float>(h_in, h_out, rows, d, ld, angular, scale, acc, per_row, stream);
+    case GRASP_DTYPE_BF16: return launch_pair<__nv_bfloat16>(h_in, h_out, rows, d, ld, angular, scale, acc, per_row, stream);
+    case GRASP_DTYPE_F16: return launch_pair<__half>(h_in, h_out, rows, d, ld, angular, scale, acc, per_row, stream);
   }
   return bad_arg("bi: dtype");
 }
 
 extern "C" int grasp_bi_chain(const void* const* hiddens, int n_states, int64_t rows, int64_t d,
-                              int64_t ld, int dtype, double* acc, void* stream) {
+                              int64_t ld, int dtype, double scale, double* acc, void* stream) {
   if (!hiddens || !acc) return bad_arg("bi_chain: null");
   if (n_states < 2 || n_states > 130) return bad_arg("bi_chain: n_states must be in [2,130]");
   if (rows < 0 || d <= 0 || ld < d) return bad_arg("bi_chain: rows/d/ld");
@@ -215,7 +215,7 @@ extern "C" int grasp_bi_chain(const void* const* hiddens, int n_states, int64_t 
   }
   if (!fast) {  // rows too wide for the register cache or unaligned: one pair launch per layer
     for (int i = 0; i + 1 < n_states; ++i) {
-      int rc = grasp_bi_accumulate(hiddens[i], hiddens[i + 1], rows, d, ld, dtype, 0, acc + i, nullptr, stream);
+      int rc = grasp_bi_accumulate(hiddens[i], hiddens[i + 1], rows, d, ld, dtype, 0, scale, acc + i, nullptr, stream);
       if (rc) return rc;
     }
     return 0;
@@ -224,13 +224,13 @@ extern "C" int grasp_bi_chain(const void* const* hiddens, int n_states, int64_t 
   for (int i = 0; i < n_states; ++i) p.h[i] = hiddens[i];
   switch (dtype) {
     case GRASP_DTYPE_F32:
-      GRASP_LAUNCH((bi_chain_kernel<float>), dim3((unsigned)rows), dim3(BI_THREADS), 0, stream, p, n_states, rows, d, ld, acc);
+      GRASP_LAUNCH((bi_chain_kernel<float>), dim3((unsigned)rows), dim3(BI_THREADS), 0, stream, p, n_states, rows, d, ld, scale, acc);
       break;
     case GRASP_DTYPE_BF16:
-      GRASP_LAUNCH((bi_chain_kernel<__nv_bfloat16>), dim3((unsigned)rows), dim3(BI_THREADS), 0, stream, p, n_states, rows, d, ld, acc);
+      GRASP_LAUNCH((bi_chain_kernel<__nv_bfloat16>), dim3((unsigned)rows), dim3(BI_THREADS), 0, stream, p, n_states, rows, d, ld, scale, acc);
       break;
     case GRASP_DTYPE_F16:
-      GRASP_LAUNCH((bi_chain_kernel<__half>), dim3((unsigned)rows), dim3(BI_THREADS), 0, stream, p, n_states, rows, d, ld, acc);
+      GRASP_LAUNCH((bi_chain_kernel<__half>), dim3((unsigned)rows), dim3(BI_THREADS), 0, stream, p, n_states, rows, d, ld, scale, acc);
       break;
     default:
       return bad_arg("bi_chain: dtype");

@@ -1,24 +1,470 @@
-// tcgen05 / TMA split-bf16 GEMM paths (GRASP_PREC_BF16X3 / BF16X6).
-// Placeholder until the tensor-core kernels are validated on hardware: every
-// entry point reports "not available" so callers fail loudly instead of
-// silently computing on another path.
-#include "common.cuh"
+// fp32-accurate GEMM on the sm_100a tensor cores.
+//
+// fp32 operands are split into NS bf16 planes (x = p0 + p1 (+ p2), each plane the bf16
+// rounding of the running remainder) by a pre-pass that also puts both operands in
+// "K-major" form  Ap[plane][m][k], Bp[plane][n][k].  The GEMM core is then
+//     C[m,n] = sum_k sum_{(i,j) in PRODUCTS} Ap[i][m,k] * Bp[j][n,k]
+// with PRODUCTS = {00,01,10} (NS=2, "BF16X3", rel. err ~4e-6) or
+// {00,01,10,11,02,20} (NS=3, "BF16X6", ~1e-7), every product a tcgen05.mma (kind::f16,
+// bf16 in, fp32 accumulate in TMEM) fed by TMA through a shared-memory ring.
+//
+// Kernel shape: persistent, one CTA per SM, 192 threads:
+//   warp 0   TMA producer (one elected lane)
+//   warp 1   TMEM allocator + MMA issuer (one elected lane)
+//   warps 2-5 epilogue (TMEM -> registers -> global)
+// The tensor core adds into its fp32 accumulator with truncation, so a long accumulation chain
+// drifts (measured: 2.8e-5 relative at K=4096 with 6 products).  Each 64-wide K block is therefore
+// accumulated into a fresh TMEM buffer (small correction products first, the hi*hi product last) and
+// the epilogue warps add the block result into fp32 registers with round-to-nearest.  The TMEM
+// buffers form a ring (512 / BN deep), so the MMA warp never waits for the epilogue.
+#include "tc_common.cuh"
 
 namespace grasp {
 
-size_t tc_gemm_workspace_bytes(int64_t, int64_t, int64_t, int) { return 0; }
-size_t tc_sigma_workspace_bytes(int64_t, int64_t, int64_t, int) { return 0; }
+using namespace tc;
 
-int tc_gemm_f32(int, int, int64_t, int64_t, int64_t, float, const float*, int64_t, const float*, int64_t, float,
-                void*, int64_t, int, int, void*, size_t, void*) {
-  set_error("tensor-core GEMM path not built in this revision");
-  return -2;
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;           // 64 bf16 = 128 bytes = one swizzle row
+constexpr int TC_THREADS = 192;
+constexpr int TC_A_TILE = TC_BM * TC_BK * 2;   // 16 KiB per plane
+
+enum { EPI_STORE = 0, EPI_SIGMA = 1 };
+
+struct TcParams {
+  int M, N, K;
+  int tiles_m, tiles_n;
+  float alpha, beta;
+  void* C;            // EPI_STORE: [M][ldc] fp32 or bf16
+  int64_t ldc;
+  int c_bf16;
+  const float* Umul;  // EPI_SIGMA: [M][ldu], multiplied element-wise before the column reduction
+  int64_t ldu;
+  float* partial;     // EPI_SIGMA: [tiles_m][N]
+};
+
+template <int NS, int BN>
+struct TcCfg {
+  static constexpr int B_TILE = BN * TC_BK * 2;
+  static constexpr int STAGE_BYTES = NS * (TC_A_TILE + B_TILE);
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;
+  static constexpr int NACC = 512 / BN;       // ring of per-K-block accumulators in TMEM
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 4 * BN * 4 /*sigma red*/ + 256;
+  static_assert(STAGES >= 2, "need at least a double-buffered ring");
+  static_assert(BN == 128, "the epilogue keeps one accumulator row of BN floats in registers");
+};
+
+template <int NS, int BN, int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcParams p) {
+  using Cfg = TcCfg<NS, BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ unsigned char smem_dyn[];
+  // 1024-byte alignment for the 128-byte swizzle atoms
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  float* red = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);   // [4][BN]
+  constexpr int NACC = Cfg::NACC;
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], acc_full[NACC], acc_empty[NACC];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kblocks = (p.K + TC_BK - 1) / TC_BK;
+  const int total_tiles = p.tiles_m * p.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA);
+    prefetch_tmap(&mapB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < NACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(&tmem_base_smem);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile % p.tiles_m) * TC_BM, n0 = (tile / p.tiles_m) * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          unsigned char* sA = smem + stage * Cfg::STAGE_BYTES;
+          unsigned char* sB = sA + NS * TC_A_TILE;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+#pragma unroll
+          for (int pl = 0; pl < NS; ++pl) {
+            tma_load_3d(sA + pl * TC_A_TILE, &mapA, &full_bar[stage], kb * TC_BK, m0, pl);
+            tma_load_3d(sB + pl * Cfg::B_TILE, &mapB, &full_bar[stage], kb * TC_BK, n0, pl);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, BN);
+      // plane products, small terms first
+      constexpr int NPROD = (NS == 2) ? 3 : 6;
+      constexpr int PA[6] = {NS == 2 ? 1 : 2, NS == 2 ? 0 : 0, NS == 2 ? 0 : 1, 1, 0, 0};
+      constexpr int PB[6] = {NS == 2 ? 0 : 0, NS == 2 ? 1 : 2, NS == 2 ? 0 : 1, 0, 1, 0};
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+          const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sB = sA + NS * TC_A_TILE;
+#pragma unroll
+          for (int q = 0; q < NPROD; ++q) {
+            const uint64_t da = umma_desc_kmajor_sw128(sA + PA[q] * TC_A_TILE);
+            const uint64_t db = umma_desc_kmajor_sw128(sB + PB[q] * Cfg::B_TILE);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              // +32 bytes per 16-element K step inside the 128-byte swizzle row
+              umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (q | k) != 0);
+            }
+          }
+          umma_commit(&empty_bar[stage]);           // frees the smem stage when the MMAs retire
+          umma_commit(&acc_full[acc]);              // this K block's partial product is complete
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int quad = warp & 3;                      // TMEM lane quadrant this warp may access
+    const int ep_tid = (int)threadIdx.x - 64;       // 0..127
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_blk = tile % p.tiles_m, n_blk = tile / p.tiles_m;
+      const int row = m_blk * TC_BM + quad * 32 + lane;
+      const int n0 = n_blk * BN;
+      float racc[BN];
+#pragma unroll
+      for (int j = 0; j < BN; ++j) racc[j] = 0.f;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&acc_full[acc], acc_phase);
+        tc_fence_after_sync();
+        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+          float t[32];
+          tmem_ld_32x32(t_row + (uint32_t)(c * 32), t);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) racc[c * 32 + j] += t[j];   // round-to-nearest fp32 add
+        }
+        tc_fence_before_sync();
+        mbar_arrive(&acc_empty[acc]);               // hand the TMEM buffer back to the MMA warp
+        if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+      }
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) {
+        float* v = &racc[c * 32];
+        const int col0 = n0 + c * 32;
+        if constexpr (EPI == EPI_STORE) {
+          if (row < p.M && col0 < p.N) {
+            const int ncols = min(32, p.N - col0);
+            if (p.c_bf16) {
+              __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.C) + (int64_t)row * p.ldc + col0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (j < ncols) {
+                  float x = p.alpha * v[j];
+                  if (p.beta != 0.f) x += p.beta * __bfloat162float(dst[j]);
+                  dst[j] = __float2bfloat16_rn(x);
+                }
+              }
+            } else {
+              float* dst = static_cast<float*>(p.C) + (int64_t)row * p.ldc + col0;
+              const bool vec = (ncols == 32) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+              if (vec) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  float4 o = make_float4(p.alpha * v[j], p.alpha * v[j + 1], p.alpha * v[j + 2], p.alpha * v[j + 3]);
+                  if (p.beta != 0.f) {
+                    const float4 old = *reinterpret_cast<const float4*>(dst + j);
+                    o.x += p.beta * old.x; o.y += p.beta * old.y; o.z += p.beta * old.z; o.w += p.beta * old.w;
+                  }
+                  *reinterpret_cast<float4*>(dst + j) = o;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  if (j < ncols) {
+                    float x = p.alpha * v[j];
+                    if (p.beta != 0.f) x += p.beta * dst[j];
+                    dst[j] = x;
+                  }
+                }
+              }
+            }
+          }
+        } else {
+          // multiply by U[row][col] and reduce over the 32 rows of this warp
+          const float* u = p.Umul + (int64_t)row * p.ldu + col0;
+          const bool row_ok = row < p.M;
+          const bool vec = row_ok && (col0 + 32 <= p.N) && ((reinterpret_cast<uintptr_t>(u) & 15) == 0);
+          if (vec) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 uu = *reinterpret_cast<const float4*>(u + j);
+              v[j] *= uu.x; v[j + 1] *= uu.y; v[j + 2] *= uu.z; v[j + 3] *= uu.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (row_ok && col0 + j < p.N) ? v[j] * u[j] : 0.f;
+          }
+          // transpose-reduce: afterwards v[0] of lane l is the sum over lanes of column l
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) {
+#pragma unroll
+            for (int j = 0; j < o; ++j) {
+              const bool up = (lane & o) != 0;
+              const float send = up ? v[j] : v[j + o];
+              const float keep = up ? v[j + o] : v[j];
+              v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+          }
+          red[quad * BN + c * 32 + lane] = v[0];
+        }
+      }
+      if constexpr (EPI == EPI_SIGMA) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int j = ep_tid; j < BN; j += 128) {
+          const int col = n0 + j;
+          if (col < p.N)
+            p.partial[(int64_t)m_blk * p.N + col] = (red[j] + red[BN + j]) + (red[2 * BN + j] + red[3 * BN + j]);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
 }
 
-int tc_sigma_partials(const float*, const float*, const float*, int64_t, int64_t, int64_t, int, float*, int64_t*,
-                      void*, size_t, void*) {
-  set_error("tensor-core sigma-score path not built in this revision");
-  return -2;
+// ---------------------------------------------------------------------------
+// split pre-pass: fp32 [rows x cols] (or its transpose) -> NS bf16 planes [NS][R][Kp]
+// ---------------------------------------------------------------------------
+template <int NS>
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16* out) {
+#pragma unroll
+  for (int i = 0; i < NS; ++i) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    out[i] = h;
+    x -= __bfloat162float(h);
+  }
+}
+
+// planes[pl][r][k] = part_pl(src[r*ld + k]),  r < R, k < K   (no transpose; 4 elements per thread)
+template <int NS>
+__global__ void split_rows_kernel(const float* __restrict__ src, int64_t ld, int R, int K, int Kp,
+                                  __nv_bfloat16* __restrict__ planes) {
+  const int r = blockIdx.y;
+  const int k0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (k0 >= Kp) return;
+  float x[4];
+  const float* s = src + (int64_t)r * ld + k0;
+  if (k0 + 3 < K && ((reinterpret_cast<uintptr_t>(s) & 15) == 0)) {
+    const float4 t = *reinterpret_cast<const float4*>(s);
+    x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x[j] = (k0 + j < K) ? s[j] : 0.f;
+  }
+  __nv_bfloat16 parts[4][NS];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split_bf16<NS>(x[j], parts[j]);
+#pragma unroll
+  for (int pl = 0; pl < NS; ++pl) {
+    __nv_bfloat16* d = planes + ((int64_t)pl * R + r) * Kp + k0;   // Kp % 8 == 0 and k0 % 4 == 0 -> 8-byte aligned
+    const __nv_bfloat162 lo = __halves2bfloat162(parts[0][pl], parts[1][pl]);
+    const __nv_bfloat162 hi = __halves2bfloat162(parts[2][pl], parts[3][pl]);
+    uint2 w;
+    w.x = *reinterpret_cast<const uint32_t*>(&lo);
+    w.y = *reinterpret_cast<const uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(d) = w;
+  }
+}
+
+// planes[pl][r][k] = part_pl(src[k*ld + r])   (source holds the transpose: K rows of length R)
+template <int NS>
+__global__ void split_transposed_kernel(const float* __restrict__ src, int64_t ld, int R, int K, int Kp,
+                                        __nv_bfloat16* __restrict__ planes) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int dy = ty; dy < 32; dy += 8) {
+    const int k = k0 + dy, r = r0 + tx;
+    tile[dy][tx] = (k < K && r < R) ? src[(int64_t)k * ld + r] : 0.f;
+  }
+  __syncthreads();
+  for (int dy = ty; dy < 32; dy += 8) {
+    const int r = r0 + dy, k = k0 + tx;
+    if (r < R && k < Kp) {
+      __nv_bfloat16 parts[NS];
+      split_bf16<NS>(tile[tx][dy], parts);
+#pragma unroll
+      for (int pl = 0; pl < NS; ++pl) planes[((int64_t)pl * R + r) * Kp + k] = parts[pl];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// planes [NS][R][Kp] bf16 -> 3-D map (k, r, plane), box 64 x box_rows x 1, 128-byte swizzle, zero OOB fill
+static int make_plane_map(CUtensorMap* map, const void* planes, int NS, int R, int K, int Kp, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return -3; }
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)R, (cuuint64_t)NS};
+  cuuint64_t strides[2] = {(cuuint64_t)Kp * 2, (cuuint64_t)R * Kp * 2};
+  cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(planes), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return -3; }
+  return 0;
+}
+
+static int kp_of(int64_t K) { return (int)round_up(K, 8); }
+static size_t planes_bytes(int NS, int64_t R, int64_t K) { return round_up((int64_t)NS * R * kp_of(K) * 2, 1024); }
+static int ns_of(int prec) { return prec == GRASP_PREC_BF16X6 ? 3 : 2; }
+
+template <int NS>
+static int split_operand(const float* src, int64_t ld, int transposed, int R, int K, __nv_bfloat16* planes, void* stream) {
+  const int Kp = kp_of(K);
+  if (!transposed) {
+    dim3 grid((unsigned)ceil_div(Kp, 4 * 256), (unsigned)R);
+    GRASP_LAUNCH((split_rows_kernel<NS>), grid, dim3(256), 0, stream, src, ld, R, K, Kp, planes);
+  } else {
+    dim3 grid((unsigned)ceil_div(Kp, 32), (unsigned)ceil_div(R, 32));
+    GRASP_LAUNCH((split_transposed_kernel<NS>), grid, dim3(32, 8), 0, stream, src, ld, R, K, Kp, planes);
+  }
+  GRASP_CHECK_LAST("split kernel");
+  return 0;
+}
+
+template <int NS, int BN, int EPI>
+static int launch_core(const __nv_bfloat16* Ap, const __nv_bfloat16* Bp, TcParams prm, void* stream) {
+  using Cfg = TcCfg<NS, BN>;
+  CUtensorMap mapA, mapB;
+  int rc = make_plane_map(&mapA, Ap, NS, prm.M, prm.K, kp_of(prm.K), TC_BM);
+  if (rc) return rc;
+  rc = make_plane_map(&mapB, Bp, NS, prm.N, prm.K, kp_of(prm.K), BN);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    rc = check_cuda(cudaFuncSetAttribute(tc_gemm_kernel<NS, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES), "tc_gemm attr");
+    if (rc) return rc;
+    attr_set = true;
+  }
+  prm.tiles_m = (int)ceil_div(prm.M, TC_BM);
+  prm.tiles_n = (int)ceil_div(prm.N, BN);
+  const int total = prm.tiles_m * prm.tiles_n;
+  const int grid = total < sm_count() ? total : sm_count();
+  GRASP_LAUNCH((tc_gemm_kernel<NS, BN, EPI>), dim3(grid), dim3(TC_THREADS), Cfg::SMEM_BYTES, stream, mapA, mapB, prm);
+  GRASP_CHECK_LAST("tc_gemm_kernel");
+  return 0;
+}
+
+size_t tc_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int prec) {
+  const int NS = ns_of(prec);
+  return planes_bytes(NS, M, K) + planes_bytes(NS, N, K) + 2048;
+}
+
+size_t tc_sigma_workspace_bytes(int64_t out, int64_t in, int64_t r, int prec) {
+  return (size_t)round_up(ceil_div(out, TC_BM) * r * 4, 1024) + tc_gemm_workspace_bytes(out, r, in, prec);
+}
+
+static bool dims_ok(int64_t M, int64_t N, int64_t K) {
+  return M > 0 && N > 0 && K > 0 && M < (1 << 30) && N < (1 << 30) && K < (1 << 30);
+}
+
+int tc_gemm_f32(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda,
+                const float* B, int64_t ldb, float beta, void* C, int64_t ldc, int c_bf16, int prec, void* ws,
+                size_t ws_bytes, void* stream) {
+  if (!dims_ok(M, N, K)) return bad_arg("tc_gemm: M/N/K");
+  if (!ws || ws_bytes < tc_gemm_workspace_bytes(M, N, K, prec)) return bad_arg("tc_gemm: workspace too small");
+  const int NS = ns_of(prec);
+  unsigned char* w = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~(uintptr_t)1023);
+  __nv_bfloat16* Ap = reinterpret_cast<__nv_bfloat16*>(w);
+  __nv_bfloat16* Bp = reinterpret_cast<__nv_bfloat16*>(w + planes_bytes(NS, M, K));
+  int rc;
+  // A: op(A) is M x K; stored [M][K] (ta=0, already K-major) or [K][M] (ta=1)
+  // B: op(B) is K x N; K-major form is [N][K]: stored [N][K] when tb=1, [K][N] when tb=0 (needs the transpose)
+  if (NS == 2) {
+    rc = split_operand<2>(A, lda, ta, (int)M, (int)K, Ap, stream); if (rc) return rc;
+    rc = split_operand<2>(B, ldb, !tb, (int)N, (int)K, Bp, stream); if (rc) return rc;
+  } else {
+    rc = split_operand<3>(A, lda, ta, (int)M, (int)K, Ap, stream); if (rc) return rc;
+    rc = split_operand<3>(B, ldb, !tb, (int)N, (int)K, Bp, stream); if (rc) return rc;
+  }
+  TcParams prm{};
+  prm.M = (int)M; prm.N = (int)N; prm.K = (int)K;
+  prm.alpha = alpha; prm.beta = beta; prm.C = C; prm.ldc = ldc; prm.c_bf16 = c_bf16;
+  if (NS == 2) return launch_core<2, 128, EPI_STORE>(Ap, Bp, prm, stream);
+  return launch_core<3, 128, EPI_STORE>(Ap, Bp, prm, stream);
+}
+
+int tc_sigma_partials(const float* U, const float* G, const float* Vh, int64_t out, int64_t in, int64_t r, int prec,
+                      float* partial, int64_t* n_partials, void* ws, size_t ws_bytes, void* stream) {
+  if (!dims_ok(out, r, in)) return bad_arg("tc_sigma: out/in/r");
+  if (ws_bytes < tc_sigma_workspace_bytes(out, in, r, prec)) return bad_arg("tc_sigma: workspace too small");
+  const int NS = ns_of(prec);
+  const int64_t tiles_m = ceil_div(out, TC_BM);
+  unsigned char* w = static_cast<unsigned char*>(ws) + round_up(tiles_m * r * 4, 1024);
+  w = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(w) + 1023) & ~(uintptr_t)1023);
+  __nv_bfloat16* Gp = reinterpret_cast<__nv_bfloat16*>(w);
+  __nv_bfloat16* Vp = reinterpret_cast<__nv_bfloat16*>(w + planes_bytes(NS, out, in));
+  int rc;
+  if (NS == 2) {
+    rc = split_operand<2>(G, in, 0, (int)out, (int)in, Gp, stream); if (rc) return rc;
+    rc = split_operand<2>(Vh, in, 0, (int)r, (int)in, Vp, stream); if (rc) return rc;
+  } else {
+    rc = split_operand<3>(G, in, 0, (int)out, (int)in, Gp, stream); if (rc) return rc;
+    rc = split_operand<3>(Vh, in, 0, (int)r, (int)in, Vp, stream); if (rc) return rc;
+  }
+  TcParams prm{};
+  prm.M = (int)out; prm.N = (int)r; prm.K = (int)in;
+  prm.alpha = 1.f; prm.beta = 0.f;
+  prm.Umul = U; prm.ldu = r; prm.partial = partial;
+  *n_partials = tiles_m;
+  if (NS == 2) return launch_core<2, 128, EPI_SIGMA>(Gp, Vp, prm, stream);
+  return launch_core<3, 128, EPI_SIGMA>(Gp, Vp, prm, stream);
 }
 
 }  // namespace grasp

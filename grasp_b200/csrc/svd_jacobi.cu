@@ -206,13 +206,20 @@ svd_evd_kernel(SvdGroup g, int round, int sweep, float tol, int inner_cap) {
         if (tid < H) {
           int p, q;
           rr_pair(JS, t, tid, p, q);
-          const double gpp = sm.G[p][p], gqq = sm.G[q][q], gpq = sm.G[p][q];
+          const float gpp = sm.G[p][p], gqq = sm.G[q][q], gpq = sm.G[p][q];
           double c = 1.0, s = 0.0;
-          if (gpq != 0.0 && fabs(gpq) > (double)tol * sqrt(fabs(gpp * gqq))) {
-            const double tau = (gqq - gpp) / (2.0 * gpq);
-            const double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-            c = 1.0 / sqrt(1.0 + tt * tt);
-            s = tt * c;
+          if (gpq != 0.f && fabsf(gpq) > tol * sqrtf(fabsf(gpp * gqq))) {
+            // the angle only steers convergence: fp32 is enough for it.  Orthogonality needs
+            // c^2 + s^2 == 1 far below fp32 rounding, so the pair is renormalised in fp64
+            // (first-order: 1/sqrt(1+d) = 1 - d/2 for d ~ 1e-7) without any fp64 div/sqrt.
+            const float tau = (gqq - gpp) / (2.f * gpq);
+            const float tt = copysignf(1.f, tau) / (fabsf(tau) + sqrtf(fmaf(tau, tau, 1.f)));
+            const float c0 = rsqrtf(fmaf(tt, tt, 1.f));
+            const float s0 = tt * c0;
+            const double cd = (double)c0, sd = (double)s0;
+            const double corr = 1.0 - 0.5 * (cd * cd + sd * sd - 1.0);
+            c = cd * corr;
+            s = sd * corr;
             sm.rotated = 1;
             sm.nonident = 1;
           }
@@ -481,7 +488,7 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
     attr_set = true;
   }
   const float tol = 5e-7f;
-  const int inner_cap = 3;
+  const int inner_cap = 8;
   cudaStream_t st = (cudaStream_t)stream;
 
   // plans + workspace carving

@@ -58,17 +58,18 @@ class BlockInfluence:
         self.stride = max(int(stride or 1), 1) if angular else 1
         self.acc = None
 
-    def add(self, hiddens: Sequence[torch.Tensor]) -> None:
+    def add(self, hiddens: Sequence[torch.Tensor], scale: float = 1.0) -> None:
         hiddens = list(hiddens)
         if self.acc is None:
             n = max(self.n_layers, len(hiddens) - 1)
             self.acc = torch.zeros(n, dtype=torch.float64, device=hiddens[0].device)
         if not self.angular:
-            ops.bi_chain(hiddens, self.acc)
+            ops.bi_chain(hiddens, self.acc, scale=scale)
             return
         # angular variant: last token only, layer i against layer i+stride
         for i in range(len(hiddens) - self.stride):
-            ops.bi_accumulate(hiddens[i][:, -1:], hiddens[i + self.stride][:, -1:], self.acc[i:i + 1], angular=True)
+            ops.bi_accumulate(hiddens[i][:, -1:], hiddens[i + self.stride][:, -1:], self.acc[i:i + 1], angular=True,
+                              scale=scale)
 
     def result(self) -> List[float]:
         if self.acc is None:
@@ -141,3 +142,216 @@ def contract_sigma_grad(layer, dsigma: torch.Tensor = None) -> torch.Tensor:
     g, _ = ops.sigma_score(layer.U.data, layer._G, layer.Vh.data, None, metric="gradient", dsigma=dsigma,
                            want_score=False)
     return g
+
+
+# =============================================================================
+# Calibration engine: layer-wise LLaMA runner with a prefix-activation cache
+# =============================================================================
+# The reference runs the whole HF model forward+backward for every calibration sample of
+# every block pass (reference modeling_grasp.py:340-354).  Layers below the block being
+# compressed are untouched originals (grasp.py:75 walks layers deepest first), so their
+# output is a constant of the run: it is computed once per selected layer and cached in HBM
+# (n_samples x seq x hidden fp32, 4.3 GB at LLaMA-2-7B / 512 x 511).  A block pass then runs
+# only layers [l, L) + norm + lm_head with autograd, in micro-batches of several samples
+# (the summed per-sample mean losses give exactly the gradient sum of the reference's
+# batch-size-1 loop).
+
+import re
+import torch.nn.functional as F
+
+_F_LINEAR = F.linear
+
+
+class _GemmLinearFn(torch.autograd.Function):
+    """y = x W^T (+ b) for a frozen weight, on grasp_gemm_f32."""
+
+    @staticmethod
+    def forward(ctx, x2d, weight):
+        ctx.weight = weight
+        return ops.gemm(x2d, weight, tb=True)
+
+    @staticmethod
+    def backward(ctx, dy):
+        if not ctx.needs_input_grad[0]:
+            return None, None
+        return ops.gemm(dy.contiguous(), ctx.weight), None
+
+
+def _routed_linear(input, weight, bias=None):
+    if (input.is_cuda and input.dtype == torch.float32 and weight.dtype == torch.float32
+            and not weight.requires_grad and input.dim() >= 2 and input.shape[-1] == weight.shape[1]):
+        x2d = input.reshape(-1, input.shape[-1])
+        if not x2d.is_contiguous():
+            x2d = x2d.contiguous()
+        y = _GemmLinearFn.apply(x2d, weight)
+        if bias is not None:
+            y = y + bias
+        return y.view(*input.shape[:-1], weight.shape[0])
+    return _F_LINEAR(input, weight, bias)
+
+
+@contextlib.contextmanager
+def grasp_linear(enabled: bool = True):
+    """Route every fp32 CUDA F.linear (and the GRASPLayer GEMMs) through grasp_gemm_f32."""
+    if not enabled:
+        yield
+        return
+    global _LINEAR_BACKEND
+    prev_backend = _LINEAR_BACKEND
+    F.linear = _routed_linear
+    torch.nn.functional.linear = _routed_linear
+    _LINEAR_BACKEND = "grasp"
+    try:
+        yield
+    finally:
+        F.linear = _F_LINEAR
+        torch.nn.functional.linear = _F_LINEAR
+        _LINEAR_BACKEND = prev_backend
+
+
+class CalibrationSet:
+    """All calibration batches of a DataLoader, resident on the device (tokens are tiny)."""
+
+    def __init__(self, dataloader, device):
+        ids, labels, weights = [], [], []
+        self.supported = True
+        for batch in dataloader:
+            if len(batch) != 2:       # attention_mask present -> generic path
+                self.supported = False
+                break
+            b = batch["input_ids"].shape[0]
+            ids.append(batch["input_ids"])
+            labels.append(batch["labels"])
+            weights += [1.0 / b] * b  # the reference averages the loss over the whole batch
+        if self.supported and ids and all(t.shape[1:] == ids[0].shape[1:] for t in ids):
+            self.input_ids = torch.cat(ids).to(device, non_blocking=True)
+            self.labels = torch.cat(labels).to(device, non_blocking=True)
+            self.weights = torch.tensor(weights, dtype=torch.float32, device=device)
+            self.n_batches = len(ids)
+        else:
+            self.supported = False
+
+    def __len__(self):
+        return self.input_ids.shape[0]
+
+
+class LlamaRunner:
+    """Runs a HF LLaMA-family causal LM layer by layer (same modules, same math as model.forward)."""
+
+    def __init__(self, hf_model, micro_batch: int = 8, use_grasp_gemm: bool = True):
+        self.hf = hf_model
+        m = hf_model.model
+        self.embed, self.layers, self.norm, self.rotary, self.head = (m.embed_tokens, m.layers, m.norm, m.rotary_emb,
+                                                                      hf_model.lm_head)
+        self.micro_batch = micro_batch
+        self.use_grasp_gemm = use_grasp_gemm
+        self.cache = {}          # layer id -> [n_samples, S, d] input of that layer
+        self.cache_key = None    # id of the CalibrationSet the cache belongs to
+
+    @staticmethod
+    def supports(hf_model) -> bool:
+        m = getattr(hf_model, "model", None)
+        ok = all(hasattr(m, a) for a in ("embed_tokens", "layers", "norm", "rotary_emb")) and hasattr(hf_model, "lm_head")
+        impl = getattr(getattr(hf_model, "config", None), "_attn_implementation", "sdpa")
+        return bool(ok and impl in ("sdpa", None))
+
+    @property
+    def n_layers(self):
+        return len(self.layers)
+
+    def _pos(self, hidden):
+        position_ids = torch.arange(hidden.shape[1], device=hidden.device).unsqueeze(0)
+        return position_ids, self.rotary(hidden, position_ids=position_ids)
+
+    def _layer(self, i, hidden, position_ids, pos_emb):
+        out = self.layers[i](hidden, attention_mask=None, position_ids=position_ids, position_embeddings=pos_emb,
+                             use_cache=False)
+        return out[0] if isinstance(out, tuple) else out
+
+    def run_layers(self, hidden, lo, hi):
+        position_ids, pos_emb = self._pos(hidden)
+        for i in range(lo, hi):
+            hidden = self._layer(i, hidden, position_ids, pos_emb)
+        return hidden
+
+    def hidden_states(self, input_ids):
+        """The L+1 states HF returns with output_hidden_states=True (last one after the final norm)."""
+        hidden = self.embed(input_ids)
+        position_ids, pos_emb = self._pos(hidden)
+        states = [hidden]
+        for i in range(self.n_layers):
+            hidden = self._layer(i, hidden, position_ids, pos_emb)
+            states.append(hidden)
+        states[-1] = self.norm(hidden)
+        return states
+
+    def loss_sum(self, hidden, labels, weights):
+        """sum_samples w_s * mean_t CE(logits[s, t], labels[s, t+1]): HF's causal-LM loss on the loader's
+        already shifted labels (the reference's double shift), one term per sample."""
+        logits = self.head(self.norm(hidden))
+        B, S, V = logits.shape
+        per_tok = F.cross_entropy(logits[:, :-1].reshape(-1, V).float(), labels[:, 1:].reshape(-1), reduction="none")
+        return (per_tok.view(B, S - 1).mean(dim=1) * weights).sum()
+
+    # ---- prefix cache -------------------------------------------------------------
+    def invalidate_above(self, layer_id: int):
+        """Layer `layer_id` changed: cached inputs of deeper layers are stale."""
+        for k in [k for k in self.cache if k > layer_id]:
+            del self.cache[k]
+
+    def build_cache(self, calib: CalibrationSet, layer_ids):
+        if self.cache_key != id(calib):
+            self.cache, self.cache_key = {}, id(calib)
+        need = sorted(set(l for l in layer_ids if l not in self.cache))
+        if not need:
+            return
+        n = len(calib)
+        with torch.no_grad(), grasp_linear(self.use_grasp_gemm):
+            for s in range(0, n, self.micro_batch):
+                ids = calib.input_ids[s:s + self.micro_batch]
+                hidden = self.embed(ids)
+                position_ids, pos_emb = self._pos(hidden)
+                for i in range(0, need[-1] + 1):
+                    if i in need:
+                        if i not in self.cache:
+                            self.cache[i] = torch.empty((n,) + tuple(hidden.shape[1:]), dtype=hidden.dtype,
+                                                        device=hidden.device)
+                        self.cache[i][s:s + ids.shape[0]] = hidden
+                    if i < need[-1]:
+                        hidden = self._layer(i, hidden, position_ids, pos_emb)
+
+    # ---- stage 1 ------------------------------------------------------------------
+    def block_influence(self, calib: CalibrationSet, scorer: "BlockInfluence"):
+        with torch.no_grad(), grasp_linear(self.use_grasp_gemm):
+            for s in range(0, len(calib), self.micro_batch):
+                ids = calib.input_ids[s:s + self.micro_batch]
+                states = self.hidden_states(ids)
+                # the reference adds one mean per DataLoader batch: sum_s w_s * mean_t(sample s)
+                w = calib.weights[s:s + ids.shape[0]]
+                if bool((w == w[0]).all()):
+                    scorer.add(states, scale=float(w[0]) * ids.shape[0])
+                else:
+                    for j in range(ids.shape[0]):
+                        scorer.add([h[j:j + 1] for h in states], scale=float(w[j]))
+
+    # ---- stage 3a -----------------------------------------------------------------
+    def sigma_gradients(self, calib: CalibrationSet, layers: dict, start_layer: int):
+        """dL/dS of the GRASPLayers in `layers` (name -> module), all of them at or above start_layer."""
+        self.build_cache(calib, [start_layer])
+        src = self.cache[start_layer]
+        with deferred_sigma_grads(layers.values()), grasp_linear(self.use_grasp_gemm):
+            for s in range(0, len(calib), self.micro_batch):
+                hidden = self.run_layers(src[s:s + self.micro_batch], start_layer, self.n_layers)
+                loss = self.loss_sum(hidden, calib.labels[s:s + self.micro_batch],
+                                     calib.weights[s:s + self.micro_batch])
+                loss.backward()
+            grads = {name: contract_sigma_grad(layer) for name, layer in layers.items()}
+        return grads
+
+
+_LAYER_RE = re.compile(r"\.layers\.(\d+)\.")
+
+
+def layer_index(name: str):
+    m = _LAYER_RE.search("." + name)
+    return int(m.group(1)) if m else None

@@ -16,7 +16,7 @@ from ._lib import (DTYPE_BF16, DTYPE_F16, DTYPE_F32, METRIC_GRADIENT, METRIC_TAY
                    PREC_SIMT, GraspLibraryError, check)
 
 # arithmetic of the GEMM-shaped stages; see include/grasp_b200.h
-_DEFAULT_PREC = PREC_SIMT
+_DEFAULT_PREC = PREC_BF16X6
 
 
 def set_default_precision(prec: int) -> None:
@@ -72,7 +72,7 @@ def launch_count() -> int:
 
 # --------------------------------------------------------------------------- BI
 def bi_accumulate(h_in: torch.Tensor, h_out: torch.Tensor, acc: Optional[torch.Tensor] = None,
-                  angular: bool = False, per_row: bool = False) -> Optional[torch.Tensor]:
+                  angular: bool = False, per_row: bool = False, scale: float = 1.0) -> Optional[torch.Tensor]:
     """acc[0] += mean_t BI(h_in[t], h_out[t]); optionally returns the per-token BI (fp32 [rows])."""
     lib = _lib.load()
     dev = _need_cuda(h_in, h_out, acc)
@@ -89,14 +89,16 @@ def bi_accumulate(h_in: torch.Tensor, h_out: torch.Tensor, acc: Optional[torch.T
         raise TypeError("acc must be a float64 device tensor")
     if acc is None and out is None:
         raise ValueError("nothing to compute: pass acc and/or per_row=True")
+    if rows == 0:
+        return out
     with torch.cuda.device(dev):
         check(lib.grasp_bi_accumulate(x.data_ptr(), y.data_ptr(), rows, d, d, _DTYPES[x.dtype], int(bool(angular)),
-                                      acc.data_ptr() if acc is not None else None,
+                                      float(scale), acc.data_ptr() if acc is not None else None,
                                       out.data_ptr() if out is not None else None, _stream()), "grasp_bi_accumulate")
     return out
 
 
-def bi_chain(hiddens: Sequence[torch.Tensor], acc: torch.Tensor) -> None:
+def bi_chain(hiddens: Sequence[torch.Tensor], acc: torch.Tensor, scale: float = 1.0) -> None:
     """acc[i] += mean_t BI(hiddens[i], hiddens[i+1]) for the L+1 hidden states of one forward pass."""
     lib = _lib.load()
     dev = _need_cuda(*hiddens, acc)
@@ -116,7 +118,7 @@ def bi_chain(hiddens: Sequence[torch.Tensor], acc: torch.Tensor) -> None:
     rows = hs[0].shape[0]
     ptrs = _lib.ptr_array([h.data_ptr() for h in hs])
     with torch.cuda.device(dev):
-        check(lib.grasp_bi_chain(ptrs, n, rows, d, d, _DTYPES[hs[0].dtype], acc.data_ptr(), _stream()),
+        check(lib.grasp_bi_chain(ptrs, n, rows, d, d, _DTYPES[hs[0].dtype], float(scale), acc.data_ptr(), _stream()),
               "grasp_bi_chain")
 
 
@@ -223,11 +225,18 @@ def topk_batched(scores: Sequence[torch.Tensor], ks: Sequence[int]) -> List[torc
     if not scores:
         return []
     sc = [_f32c(s.reshape(-1), "score") for s in scores]
+    for s, k in zip(sc, ks):
+        if not 0 <= int(k) <= s.numel():
+            raise ValueError(f"k={k} out of range for {s.numel()} scores")
     outs = [torch.empty(int(k), dtype=torch.int64, device=dev) for k in ks]
-    with torch.cuda.device(dev):
-        check(lib.grasp_topk_batched(len(sc), _lib.ptr_array([s.data_ptr() for s in sc]),
-                                     _lib.i64_array([s.numel() for s in sc]), _lib.i64_array(ks),
-                                     _lib.ptr_array([o.data_ptr() for o in outs]), _stream()), "grasp_topk_batched")
+    live = [i for i, k in enumerate(ks) if int(k) > 0]
+    if live:
+        with torch.cuda.device(dev):
+            check(lib.grasp_topk_batched(len(live), _lib.ptr_array([sc[i].data_ptr() for i in live]),
+                                         _lib.i64_array([sc[i].numel() for i in live]),
+                                         _lib.i64_array([ks[i] for i in live]),
+                                         _lib.ptr_array([outs[i].data_ptr() for i in live]), _stream()),
+                  "grasp_topk_batched")
     return outs
 
 

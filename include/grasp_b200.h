@@ -57,21 +57,22 @@ uint64_t    grasp_launch_count(void);
  * (block_influence) as called from modeling_grasp.py:163-167: per token row t
  *   sim_t = <x_t,y_t>/(|x_t||y_t|), NaN -> 0.5, bi_t = 1-sim_t
  *   (angular != 0: bi_t = arccos(sim_t)/pi)
- * and *acc += mean_t(bi_t)  (acc is a device double, so the per-batch sums the
- * reference keeps in Python floats stay on the device).  per_row (nullable)
+ * and *acc += scale * mean_t(bi_t)  (acc is a device double, so the per-batch sums
+ * the reference keeps in Python floats stay on the device; scale = 1 reproduces the
+ * reference, other values re-weight a launch that carries several batches).  per_row (nullable)
  * receives bi_t as fp32 [rows].  ld = row stride in elements.
  * ------------------------------------------------------------------------- */
 int grasp_bi_accumulate(const void* h_in, const void* h_out, int64_t rows, int64_t d,
-                        int64_t ld, int dtype, int angular,
+                        int64_t ld, int dtype, int angular, double scale,
                         double* acc, float* per_row, void* stream);
 
 /* (a2) the whole chain of one forward pass: hiddens[0..n_states) are the
  * L+1 hidden states of modeling_grasp.py:180-183 (HOST array of device
- * pointers, each [rows, d] with row stride ld); acc[i] += mean_t BI(h[i],h[i+1])
+ * pointers, each [rows, d] with row stride ld); acc[i] += scale * mean_t BI(h[i],h[i+1])
  * for i in [0, n_states-1).  Every hidden state is read from HBM exactly once.
  * n_states <= 130. */
 int grasp_bi_chain(const void* const* hiddens, int n_states, int64_t rows, int64_t d,
-                   int64_t ld, int dtype, double* acc, void* stream);
+                   int64_t ld, int dtype, double scale, double* acc, void* stream);
 
 /* ---------------------------------------------------------------------------
  * (a3) thin SVD, replaces torch.linalg.svd(w, full_matrices=False) at

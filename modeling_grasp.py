@@ -12,6 +12,7 @@ the sm_100a kernels of grasp_b200 (no torch.linalg.svd / torch.topk / CPU path):
   compile_grasp_model        -> low-rank rebuild GEMM / sqrt(S) factor pack
 """
 import logging
+import os
 from typing import Dict, List, Literal, Optional, Union
 
 import numpy as np
@@ -130,6 +131,49 @@ class GRASPModel(nn.Module):
             p.requires_grad = False
         self.grasp_values_dict = {}
         self._svd_cache: Dict[str, tuple] = {}
+        # B200 engine state (not part of the reference surface)
+        self.use_engine = os.environ.get("GRASP_B200_ENGINE", "1") != "0"
+        self.micro_batch = int(os.environ.get("GRASP_B200_MICRO_BATCH", "8"))
+        self._runner = None
+        self._calib = None
+
+    def __getstate__(self):
+        # caches and the runner hold device tensors / module references that do not belong in a checkpoint
+        state = self.__dict__.copy()
+        state["_runner"], state["_calib"], state["_svd_cache"] = None, None, {}
+        return state
+
+    # ------------------------------------------------------------------ B200 engine plumbing
+    def _engine_runner(self):
+        """Layer-wise runner with the prefix-activation cache, or None when the wrapped model is not a
+        LLaMA-family causal LM (then the generic whole-model path is used)."""
+        if not self.use_engine or not engine.LlamaRunner.supports(self.model):
+            return None
+        if self._runner is None:
+            self._runner = engine.LlamaRunner(self.model, micro_batch=self.micro_batch)
+        return self._runner
+
+    def _calibration_set(self, dataloader, device):
+        if self._calib is None or self._calib[0] is not dataloader:
+            self._calib = (dataloader, engine.CalibrationSet(dataloader, device))
+        return self._calib[1]
+
+    def _touched(self, module_name: str):
+        idx = engine.layer_index(module_name)
+        if self._runner is not None and idx is not None:
+            self._runner.invalidate_above(idx)
+
+    def prepare_calibration(self, calibration_dataloader, layers_id, device="cuda"):
+        """Cache, in one forward sweep, the hidden state entering every layer of `layers_id` for all
+        calibration samples, so each later block pass starts at its own layer."""
+        runner = self._engine_runner()
+        if runner is None:
+            return False
+        calib = self._calibration_set(calibration_dataloader, device)
+        if not calib.supported:
+            return False
+        runner.build_cache(calib, list(layers_id))
+        return True
 
     # ------------------------------------------------------------------ misc (API parity)
     def calculate_layer_compression_ratio(self, redundant_layers: Optional[List] = None):
@@ -170,8 +214,12 @@ class GRASPModel(nn.Module):
         n_layers = len(self.model.model.layers)
         logger.info("=======>Compute Block Influence")
         scorer = engine.BlockInfluence(n_layers, angular=angular, stride=num_prune_layers if angular else 1)
+        runner = self._engine_runner() if (hiddens is None and not angular) else None
+        calib = self._calibration_set(calibration_dataloader, device) if runner is not None else None
         if hiddens is not None:
             scorer.add(hiddens)
+        elif runner is not None and calib.supported:
+            runner.block_influence(calib, scorer)
         else:
             for batch in tqdm(calibration_dataloader, desc="Compute BI", total=len(calibration_dataloader), leave=True):
                 attention_mask = None if len(batch) == 2 else batch["attention_mask"].to(device=device)
@@ -241,6 +289,7 @@ class GRASPModel(nn.Module):
         grasp_layer = GRASPLayer(U=U, S=S, Vh=Vh, bias=module.bias,
                                  compression_ratio=getattr(module, "compression_ratio", None), weight=w)
         self._set_module(self.model, target_layer, grasp_layer)
+        self._touched(target_layer)
 
     _BLOCKS = {
         "attention": ("self_attn.", ["q_proj", "k_proj", "v_proj", "o_proj"]),
@@ -314,6 +363,14 @@ class GRASPModel(nn.Module):
         names = self.check_exists_grasp_layer()
         layers = {name: self.model.get_submodule(name) for name in names}
         self.model.to(device=device)
+        runner = self._engine_runner() if names else None
+        if runner is not None:
+            calib = self._calibration_set(calibration_dataloader, device)
+            starts = [engine.layer_index(n) for n in names]
+            if calib.supported and all(i is not None for i in starts):
+                grads = runner.sigma_gradients(calib, layers, min(starts))
+                self.grasp_layer_grads = grads
+                return grads
         with engine.deferred_sigma_grads(layers.values()):
             for batch in tqdm(calibration_dataloader, desc="Gradients Collection",
                               total=len(calibration_dataloader), leave=True):
@@ -406,5 +463,6 @@ class GRASPModel(nn.Module):
                                     sigma_fuse=sigma_fuse)
                 new.requires_grad_(False)
                 self._set_module(self.model, name, new)
+            self._touched(name)
             del layer
         return

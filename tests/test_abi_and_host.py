@@ -34,7 +34,7 @@ def test_bad_arguments_are_rejected_before_any_launch():
     before = lib.grasp_launch_count()
     assert lib.grasp_topk_batched(-1, None, None, None, None, None) < 0
     assert b"batch" in lib.grasp_last_error()
-    assert lib.grasp_bi_accumulate(None, None, 4, 8, 8, 0, 0, None, None, None) < 0
+    assert lib.grasp_bi_accumulate(None, None, 4, 8, 8, 0, 0, 1.0, None, None, None) < 0
     assert lib.grasp_svd_batched(1, None, None, None, None, None, None, None, None, 0, 0, None, 0, None) < 0
     assert lib.grasp_sigma_score(None, None, None, None, 4, 4, 4, 1, 0, None, None, 0, None, 0, None) < 0
     assert lib.grasp_lowrank_rebuild(None, None, None, None, 1, 4, 4, 4, 0, None, 0, None, 0, None) < 0

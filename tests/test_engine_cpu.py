@@ -1,0 +1,55 @@
+"""CPU: host-side logic of the calibration engine that does not touch a kernel -- the layer-wise runner
+reproduces HF's own forward (hidden states, loss with the reference's double label shift)."""
+import torch
+
+from grasp_b200 import engine, synth
+
+
+def test_runner_matches_hf_forward_and_loss():
+    model = synth.random_llama("tiny", seed=3)
+    assert engine.LlamaRunner.supports(model)
+    runner = engine.LlamaRunner(model, micro_batch=2, use_grasp_gemm=False)
+    tokens = synth.random_tokens(3, 20, 256, seed=1)
+    ids, labels = tokens[:, :-1], tokens[:, 1:]
+    with torch.no_grad():
+        out = model(input_ids=ids, labels=labels, output_hidden_states=True, use_cache=False, return_dict=True)
+        states = runner.hidden_states(ids)
+    assert len(states) == len(out.hidden_states) == model.config.num_hidden_layers + 1
+    for a, b in zip(states, out.hidden_states):
+        assert torch.allclose(a, b, atol=1e-5, rtol=1e-5)
+    # batch loss of HF == mean over samples of the per-sample means (equal lengths)
+    with torch.no_grad():
+        hidden = runner.run_layers(runner.embed(ids), 0, runner.n_layers)
+        w = torch.full((3,), 1.0 / 3)
+        loss = runner.loss_sum(hidden, labels, w)
+    assert abs(loss.item() - out.loss.item()) < 1e-5
+    # per-sample losses (reference batch size 1) add up
+    with torch.no_grad():
+        singles = sum(model(input_ids=ids[i:i + 1], labels=labels[i:i + 1], use_cache=False)[0].item() for i in range(3))
+        loss1 = runner.loss_sum(hidden, labels, torch.ones(3))
+    assert abs(loss1.item() - singles) < 1e-4
+
+
+def test_prefix_cache_equals_full_forward_and_invalidation():
+    model = synth.random_llama("tiny", seed=4)
+    runner = engine.LlamaRunner(model, micro_batch=2, use_grasp_gemm=False)
+    dl = synth.calibration_dataloader(5, 12, 256, batch_size=1, seed=2)
+    calib = engine.CalibrationSet(dl, "cpu")
+    assert calib.supported and len(calib) == 5 and calib.n_batches == 5
+    assert torch.all(calib.weights == 1.0)
+    runner.build_cache(calib, [1, 3])
+    with torch.no_grad():
+        states = runner.hidden_states(calib.input_ids)
+    assert torch.allclose(runner.cache[1], states[1], atol=1e-5)
+    assert torch.allclose(runner.cache[3], states[3], atol=1e-5)
+    runner.invalidate_above(2)
+    assert 1 in runner.cache and 3 not in runner.cache
+    dl2 = synth.calibration_dataloader(4, 12, 256, batch_size=2, seed=2)
+    calib2 = engine.CalibrationSet(dl2, "cpu")
+    assert torch.all(calib2.weights == 0.5)
+
+
+def test_layer_index_parsing():
+    assert engine.layer_index("model.layers.17.mlp.down_proj") == 17
+    assert engine.layer_index("layers.3.self_attn.q_proj") == 3
+    assert engine.layer_index("lm_head") is None
