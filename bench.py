@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the GRASP compression hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (our arm; torchrun launches it for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  (the reference's CPU path on the host cores)
+
+Workload (BASELINE.json configs[1]): random-init LLaMA-2-7B shapes, COMPRESSION_RATIO=0.9, 512 synthetic
+calibration samples x 512 tokens, fp32.  One STEP = one pruned decoder layer compressed end to end
+(7 weight matrices: SVD, two sigma-gradient passes over all calibration samples, selection, compile);
+the layer-scoring stage (block influence over all samples) and the prefix-activation sweep run once and
+are inside the timed region, so K steps = the whole NUM_PRUNE_LAYERS=K job (K=8 is configs[1] itself).
+metric = weight matrices compressed per second = 7K / wall time of the job.
+
+The timed region is the public API call a user makes -- grasp.compress(GRASPModel, DataLoader, ...) --
+with the calibration tokens in pinned HOST memory (e2e).  `value` is the same run with the separately
+event-timed host->device copy of the tokens taken out.  Times are CUDA events on the launching stream,
+barrier + synchronize on both sides, max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "weight_matrices_compressed_per_sec"
+UNIT = "matrices/s"
+MATRICES_PER_LAYER = 7
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=8, help="pruned layers compressed in the timed region")
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    p.add_argument("--model", default="llama2-7b")
+    p.add_argument("--samples", type=int, default=512)
+    p.add_argument("--seq-len", type=int, default=512)
+    p.add_argument("--ratio", type=float, default=0.9)
+    p.add_argument("--micro-batch", type=int, default=8)
+    p.add_argument("--warmup-samples", type=int, default=32)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-svd-dim", type=int, default=0, help="override the CPU sample's matrix size (debug)")
+    return p.parse_args()
+
+
+def workload_name(a):
+    return (f"random-init {a.model}, NUM_PRUNE_LAYERS={a.steps}, COMPRESSION_RATIO={a.ratio}, "
+            f"{a.samples} samples x {a.seq_len} tokens, fp32")
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [v for v in sm if v > 0.5 * (max(mx) if mx else 1)] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_sample(a, threads: int):
+    """Time the reference's CPU path (oracle port of modeling_grasp.py on torch CPU fp32) on a bounded
+    sample of the workload and extrapolate to the whole job.  Returns (dict, seconds_for_whole_job)."""
+    from grasp_b200 import synth
+    from oracle import restate
+    torch.set_num_threads(threads)
+    cfg = dict(synth.MODEL_CONFIGS[a.model])
+    d, ff, L, V = cfg["hidden_size"], cfg["intermediate_size"], cfg["num_hidden_layers"], cfg["vocab_size"]
+    if a.cpu_svd_dim:
+        d, ff = a.cpu_svd_dim, a.cpu_svd_dim * 11 // 4
+        cfg.update(hidden_size=d, intermediate_size=ff, num_attention_heads=max(1, d // 128),
+                   num_key_value_heads=max(1, d // 128))
+    # (1) the SVD of one attention-shaped matrix (reference modeling_grasp.py:231)
+    W = torch.randn(d, d) * 0.02
+    t0 = time.perf_counter()
+    U, S, Vh = restate.svd(W)
+    t_svd = time.perf_counter() - t0
+    # (2) one calibration sample through a one-layer model of the same widths: dense forward, then the
+    #     reference's GRASPLayer forward+backward for the attention block and the MLP block
+    model = synth.random_llama(a.model, seed=0, num_hidden_layers=1, **{k: cfg[k] for k in
+                               ("hidden_size", "intermediate_size", "num_attention_heads", "num_key_value_heads")})
+    for p in model.parameters():
+        p.requires_grad = False
+    tok = synth.random_tokens(1, a.seq_len, V, seed=1)
+    batch = restate.batches_from_tokens(tok)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        model(input_ids=batch[0]["input_ids"], use_cache=False)
+        t_fwd_layer_head = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        h = model.model.embed_tokens(batch[0]["input_ids"])
+        pos = torch.arange(h.shape[1]).unsqueeze(0)
+        model.model.layers[0](h, position_ids=pos, position_embeddings=model.model.rotary_emb(h, position_ids=pos))
+        t_fwd_layer = time.perf_counter() - t0
+    # attention block with the already measured SVD reused for all four projections (same shape)
+    for name in restate.block_names(0, "attention", ["q_proj", "k_proj", "v_proj", "o_proj"]):
+        lin = model.get_submodule(name)
+        if lin.weight.shape == W.shape:
+            restate._set_module(model, name, restate.OracleGRASPLayer(U, S, Vh))
+    t0 = time.perf_counter()
+    restate.svdlayer_gradients(model, batch)
+    t_pass_attn = time.perf_counter() - t0
+    n_layers_in_attn = len(restate.grasp_layer_names(model))
+    sample = {"svd_s": t_svd, "fwd_layer_s": t_fwd_layer, "fwd_layer_plus_head_s": t_fwd_layer_head,
+              "attn_block_fwd_bwd_s": t_pass_attn, "grasp_layers_in_attn_sample": n_layers_in_attn}
+    # extrapolation to the whole job (labelled as such): per selected layer 4 attention SVDs + 3 MLP SVDs
+    # (MLP cost scaled by the nominal flop ratio), 2 passes x samples x (forward of all layers + block
+    # forward/backward), plus the BI forward of every sample.
+    from grasp_b200.dist import svd_cost
+    mlp_ratio = svd_cost(ff, d) / svd_cost(d, d)
+    t_svd_layer = t_svd * (4 + 3 * mlp_ratio)
+    t_head = max(t_fwd_layer_head - t_fwd_layer, 0.0)
+    t_full_fwd = L * t_fwd_layer + t_head
+    t_pass_sample = (L - 1) * t_fwd_layer + t_pass_attn            # MLP passes cost at least the attention ones
+    total = a.steps * (t_svd_layer + 2 * a.samples * t_pass_sample) + a.samples * t_full_fwd
+    sample["extrapolated_job_s"] = total
+    return sample, total
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    times = []
+    sample = None
+    for i in range(a.warmup + a.steps):
+        t0 = time.perf_counter()
+        sample, total = cpu_reference_sample(a, threads)
+        dt = time.perf_counter() - t0
+        if i >= a.warmup:
+            times.append((dt, total))
+        if i == 0 and dt * (a.warmup + a.steps) > 240:     # keep the arm within a few minutes
+            a.steps, a.warmup = max(1, min(a.steps, int(180 / dt))), 0
+            times = [(dt, total)]
+            break
+    total = statistics.median(t for _, t in times)
+    value = MATRICES_PER_LAYER * a.steps / total
+    desc = ("per step: torch.linalg.svd of one %dx%d fp32 matrix + 1 calibration sample (dense forward of one layer "
+            "+ reference GRASPLayer attention-block forward/backward) on a 1-layer model of the named widths; "
+            "whole job extrapolated: 4+3x(MLP flop ratio) SVDs per layer, 2 passes x %d samples x (31 dense layer "
+            "forwards + block pass), BI forward of every sample") % (
+                a.cpu_svd_dim or 4096, a.cpu_svd_dim or 4096, a.samples)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1000.0 * total / a.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": workload_name(a), "extrapolated": True, "primitives": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------- our arm
+class StageTimer:
+    """CUDA-event timers around the public GRASPModel stage methods (same stream as the kernels)."""
+
+    def __init__(self):
+        self.spans = []
+
+    def wrap(self, obj, name, stage):
+        fn = getattr(obj, name)
+
+        def timed(*args, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*args, **kw)
+            e1.record()
+            self.spans.append((stage, e0, e1))
+            return out
+        setattr(obj, name, timed)
+
+    def totals(self):
+        out = {}
+        for stage, e0, e1 in self.spans:
+            out[stage] = out.get(stage, 0.0) + e0.elapsed_time(e1)
+        return out
+
+
+def run_ours(a):
+    import torch.distributed as td
+    from grasp_b200 import dist, engine, ops, synth
+    import grasp
+    from modeling_grasp import GRASPModel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        td.init_process_group("nccl", device_id=dev)
+
+    cfg = synth.MODEL_CONFIGS[a.model]
+    V, L = cfg["vocab_size"], cfg["num_hidden_layers"]
+    model = synth.random_llama(a.model, seed=0, device=dev)             # identical replicas (same seed)
+    tokens = synth.random_tokens(a.samples, a.seq_len, V, seed=0).pin_memory()
+    gm = GRASPModel(model)
+    gm.micro_batch = a.micro_batch
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up: W untimed layer steps on the deepest layer (restored afterwards), fewer samples
+    wtok = tokens[: min(a.warmup_samples, a.samples)]
+    last = f"model.layers.{L - 1}"
+    for _ in range(a.warmup):
+        saved = {n: m for n, m in model.named_modules() if n.startswith(last + ".") and n.count(".") == 4}
+        wdl = synth.calibration_dataloader(0, 0, 0, tokens=wtok)
+        grasp.compress(gm, wdl, layers_id=[L - 1], compression_ratio=a.ratio, device=dev)
+        for n, m in saved.items():
+            gm._set_module(model, n, m)
+        gm._runner, gm._calib, gm._svd_cache = None, None, {}
+    if a.warmup:
+        # the layer-scoring forward also gets warm
+        wdl = synth.calibration_dataloader(0, 0, 0, tokens=wtok)
+        gm.compute_bi(num_prune_layers=1, calibration_dataloader=wdl, device=dev)
+        gm._runner, gm._calib = None, None
+    torch.cuda.empty_cache()
+
+    # ---- timed region: the public API call with host-resident tokens
+    timer = StageTimer()
+    for name, stage in (("compute_bi", "layer_scoring"), ("precompute_svd", "svd"),
+                        ("prepare_calibration", "prefix_cache"), ("get_svdlayer_gradients", "sigma_gradients"),
+                        ("dynamic_svd_selection", "selection"), ("compile_grasp_model", "compile")):
+        timer.wrap(gm, name, stage)
+    ops.timers.reset(enabled=True)
+    dl = synth.calibration_dataloader(0, 0, 0, tokens=tokens)
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    launches0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    grasp.compress(gm, dl, num_prune_layers=a.steps, compression_ratio=a.ratio, device=dev)
+    kept = {n: (v if torch.is_tensor(v) else torch.as_tensor(v)).cpu() for n, v in gm.indices_dict.items()}  # D2H of the result
+    e1.record()
+    barrier()
+    clk = clocks.stop()
+    launches = ops.launch_count() - launches0
+    total_ms = e0.elapsed_time(e1)
+    calib = gm._calib[1]
+    h2d_ms = getattr(calib, "h2d_ms", 0.0)
+    t = torch.tensor([total_ms, total_ms - h2d_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+    total_ms, resident_ms = t.tolist()
+
+    if rank == 0:
+        n_mat = MATRICES_PER_LAYER * a.steps
+        stages = timer.totals()
+        kt = ops.timers.summary()
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        roof = None
+        if kt:
+            tag, rec = max(kt.items(), key=lambda kv: kv[1]["ms"])
+            peak = peaks.get("bf16_tflops_sustained", 1400.0)
+            achieved = rec["flops"] / (rec["ms"] * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": tag, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
+                    "launches": rec["n"], "avg_launch_ms": rec["ms"] / max(rec["n"], 1),
+                    "issued_mma_tflops": achieved * rec["mma_per_flop"],
+                    "issued_mma_frac": achieved * rec["mma_per_flop"] / peak,
+                    "share_of_step": rec["ms"] / total_ms,
+                    "all_kernels_ms": {k: round(v["ms"], 3) for k, v in kt.items()}}
+        h2d = 2 * a.samples * (a.seq_len - 1) * 8
+        d2h = sum(v.numel() * 8 for v in kept.values()) + L * 8
+        line = {"metric": METRIC, "value": n_mat / (resident_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": total_ms / a.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32 (bf16x6 split tensor-core GEMMs, fp32 accumulate; fp32 CUDA-core SVD)",
+                "data": "synthetic",
+                "config": {"workload": workload_name(a), "micro_batch": a.micro_batch,
+                           "l2": "inputs larger than L2 (27 GB of weights, 4.3 GB activation cache per layer)",
+                           "warmup_samples": min(a.warmup_samples, a.samples), "layers_chosen": gm.redundant_layers,
+                           "stages_ms": {k: round(v, 2) for k, v in stages.items()}, "end_to_end_s": total_ms / 1e3},
+                "e2e": {"value": n_mat / (total_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d // a.steps,
+                        "d2h_bytes_per_step": d2h // a.steps},
+                "gpu_launches": int(launches), "clocks": clk, "roofline": roof}
+        if not a.no_cpu_baseline and world == 1:
+            sample, cpu_total = cpu_reference_sample(a, os.cpu_count() or 1)
+            line["cpu_baseline"] = {"value": MATRICES_PER_LAYER * a.steps / cpu_total, "unit": UNIT,
+                                    "cores": os.cpu_count() or 1, "kind": "port",
+                                    "sample": "oracle/restate.py on the host cores: one 4096x4096 torch.linalg.svd + "
+                                              "1 calibration sample through a 1-layer model of the named widths "
+                                              "(dense forward, GRASPLayer attention-block forward/backward); "
+                                              "whole job extrapolated (see bench.py cpu_reference_sample)",
+                                    "primitives": sample}
+        print(json.dumps(line))
+    if world > 1:
+        td.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,104 @@
+"""Multi-GPU plan of the hot path (one process per GPU, torch.distributed over NCCL/NVLink).
+
+The reference is single-process; this partitioning is new:
+
+  SVD + rebuild     independent weight matrices -> ranks (longest-processing-time on the nominal
+                    SVD flop count), then each matrix's factors are broadcast from its owner
+  BI / sigma-grads  calibration samples -> ranks (contiguous shards); the per-layer BI sums and the
+                    per-block sigma-gradient vectors are summed with ONE all-reduce each
+  selection/compile replicated: every rank holds the same scores, so the replicas stay identical
+
+Everything is a no-op when torch.distributed is not initialised (single GPU).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence, Tuple
+
+import torch
+import torch.distributed as td
+
+
+def initialized() -> bool:
+    return td.is_available() and td.is_initialized()
+
+
+def rank_world() -> Tuple[int, int]:
+    if initialized():
+        return td.get_rank(), td.get_world_size()
+    return 0, 1
+
+
+def svd_cost(m: int, n: int) -> float:
+    """Nominal thin-SVD work 8 m n^2 + 4/3 n^3 with n = min side."""
+    big, small = max(m, n), min(m, n)
+    return 8.0 * big * small * small + 4.0 / 3.0 * small ** 3
+
+
+def partition_lpt(costs: Sequence[float], n_parts: int) -> List[List[int]]:
+    """Longest-processing-time-first assignment of items to parts; deterministic on every rank."""
+    parts: List[List[int]] = [[] for _ in range(n_parts)]
+    load = [0.0] * n_parts
+    for i in sorted(range(len(costs)), key=lambda i: (-costs[i], i)):
+        p = min(range(n_parts), key=lambda p: (load[p], p))
+        parts[p].append(i)
+        load[p] += costs[i]
+    for p in parts:
+        p.sort()
+    return parts
+
+
+def owners_of(shapes: Sequence[Tuple[int, int]], world: int) -> List[int]:
+    """Owner rank of every matrix."""
+    owner = [0] * len(shapes)
+    for r, items in enumerate(partition_lpt([svd_cost(m, n) for m, n in shapes], world)):
+        for i in items:
+            owner[i] = r
+    return owner
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [lo, hi) shard of n samples for `rank` (sizes differ by at most one)."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def all_reduce_sum_(t: torch.Tensor) -> torch.Tensor:
+    if initialized() and td.get_world_size() > 1:
+        td.all_reduce(t, op=td.ReduceOp.SUM)
+    return t
+
+
+def all_reduce_sum_many_(tensors: Sequence[torch.Tensor]) -> None:
+    """One collective for a list of same-dtype vectors (the sigma-gradients of a block: 48-64 KB)."""
+    if not (initialized() and td.get_world_size() > 1) or not tensors:
+        return
+    flat = torch.cat([t.reshape(-1) for t in tensors])
+    td.all_reduce(flat, op=td.ReduceOp.SUM)
+    off = 0
+    for t in tensors:
+        t.copy_(flat[off:off + t.numel()].view_as(t))
+        off += t.numel()
+
+
+def exchange_factors(local: Dict[int, Tuple[torch.Tensor, torch.Tensor, torch.Tensor]],
+                     shapes: Sequence[Tuple[int, int]], owner: Sequence[int], device, dtype=torch.float32):
+    """Every rank ends up with (U, S, Vh) of every matrix: owners send, the others receive."""
+    rank, world = rank_world()
+    out = []
+    pending = []
+    for i, (m, n) in enumerate(shapes):
+        r = min(m, n)
+        if owner[i] == rank:
+            U, S, Vh = local[i]
+        else:
+            U = torch.empty(m, r, dtype=dtype, device=device)
+            S = torch.empty(r, dtype=dtype, device=device)
+            Vh = torch.empty(r, n, dtype=dtype, device=device)
+        if world > 1:
+            for t in (U, S, Vh):
+                pending.append(td.broadcast(t, src=owner[i], async_op=True))
+        out.append((U, S, Vh))
+    for w in pending:
+        w.wait()
+    return out

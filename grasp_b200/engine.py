@@ -18,7 +18,7 @@ from typing import Iterable, List, Sequence
 
 import torch
 
-from . import ops
+from . import dist, ops
 
 # "torch": the three linear GEMMs of a GRASPLayer go through torch.matmul (cuBLAS fp32);
 # "grasp": they go through grasp_gemm_f32 (split-bf16 tcgen05 path of this library).
@@ -74,11 +74,24 @@ class BlockInfluence:
     def result(self) -> List[float]:
         if self.acc is None:
             return [0.0] * self.n_layers
+        dist.all_reduce_sum_(self.acc)      # multi-GPU: ranks scored disjoint sample shards
         return self.acc[: self.n_layers].cpu().tolist()
 
 
 def batched_svd(weights: Sequence[torch.Tensor], max_group: int = 8):
-    """SVD of every weight; same-shape matrices share launches (latency-bound eigen-solves overlap)."""
+    """SVD of every weight; same-shape matrices share launches (latency-bound eigen-solves overlap).
+    Multi-GPU: matrices are split over the ranks and the factors broadcast from their owners."""
+    rank, world = dist.rank_world()
+    if world > 1 and len(weights) > 0:
+        shapes = [tuple(w.shape) for w in weights]
+        owner = dist.owners_of(shapes, world)
+        mine = [i for i in range(len(weights)) if owner[i] == rank]
+        local = dict(zip(mine, _batched_svd_local([weights[i] for i in mine], max_group)))
+        return dist.exchange_factors(local, shapes, owner, weights[0].device)
+    return _batched_svd_local(weights, max_group)
+
+
+def _batched_svd_local(weights: Sequence[torch.Tensor], max_group: int = 8):
     groups: "OrderedDict[tuple, list]" = OrderedDict()
     for i, w in enumerate(weights):
         groups.setdefault(tuple(w.shape), []).append(i)
@@ -224,10 +237,23 @@ class CalibrationSet:
             labels.append(batch["labels"])
             weights += [1.0 / b] * b  # the reference averages the loss over the whole batch
         if self.supported and ids and all(t.shape[1:] == ids[0].shape[1:] for t in ids):
-            self.input_ids = torch.cat(ids).to(device, non_blocking=True)
-            self.labels = torch.cat(labels).to(device, non_blocking=True)
-            self.weights = torch.tensor(weights, dtype=torch.float32, device=device)
+            all_ids, all_labels = torch.cat(ids), torch.cat(labels)
+            self.n_total = all_ids.shape[0]
             self.n_batches = len(ids)
+            # multi-GPU: every rank keeps a contiguous shard of the samples (sums are all-reduced later)
+            rank, world = dist.rank_world()
+            lo, hi = dist.shard_range(self.n_total, rank, world)
+            on_cuda = torch.device(device).type == "cuda"
+            if on_cuda:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            self.input_ids = all_ids[lo:hi].to(device, non_blocking=True)
+            self.labels = all_labels[lo:hi].to(device, non_blocking=True)
+            self.weights = torch.tensor(weights[lo:hi], dtype=torch.float32).to(device, non_blocking=True)
+            if on_cuda:
+                e1.record()
+                e1.synchronize()
+                self.h2d_ms = e0.elapsed_time(e1)
         else:
             self.supported = False
 
@@ -346,6 +372,8 @@ class LlamaRunner:
                                      calib.weights[s:s + self.micro_batch])
                 loss.backward()
             grads = {name: contract_sigma_grad(layer) for name, layer in layers.items()}
+        # multi-GPU: each rank contracted the G of its own samples; dL/dS is linear in G
+        dist.all_reduce_sum_many_(list(grads.values()))
         return grads
 
 

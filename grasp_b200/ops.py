@@ -70,6 +70,51 @@ def launch_count() -> int:
     return int(_lib.load().grasp_launch_count())
 
 
+class _Timers:
+    """Optional CUDA-event timing of the C-ABI calls (bench.py's roofline numbers).  Off by default."""
+
+    def __init__(self):
+        self.enabled = False
+        self.spans = {}
+
+    def reset(self, enabled: bool = False):
+        self.enabled = enabled
+        self.spans = {}
+
+    def start(self):
+        if not self.enabled:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def stop(self, tag: str, e0, flops: float = 0.0, bytes_: float = 0.0, mma_per_flop: float = 1.0):
+        if e0 is None:
+            return
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        rec = self.spans.setdefault(tag, {"events": [], "flops": 0.0, "bytes": 0.0, "mma_per_flop": mma_per_flop})
+        rec["events"].append((e0, e1))
+        rec["flops"] += flops
+        rec["bytes"] += bytes_
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for tag, rec in self.spans.items():
+            ms = sum(a.elapsed_time(b) for a, b in rec["events"])
+            out[tag] = {"ms": ms, "n": len(rec["events"]), "flops": rec["flops"], "bytes": rec["bytes"],
+                        "mma_per_flop": rec["mma_per_flop"]}
+        return out
+
+
+timers = _Timers()
+
+
+def _mma_per_flop(prec: int) -> float:
+    return {PREC_SIMT: 0.0, PREC_BF16X3: 3.0, PREC_BF16X6: 6.0}[prec]
+
+
 # --------------------------------------------------------------------------- BI
 def bi_accumulate(h_in: torch.Tensor, h_out: torch.Tensor, acc: Optional[torch.Tensor] = None,
                   angular: bool = False, per_row: bool = False, scale: float = 1.0) -> Optional[torch.Tensor]:
@@ -118,8 +163,10 @@ def bi_chain(hiddens: Sequence[torch.Tensor], acc: torch.Tensor, scale: float = 
     rows = hs[0].shape[0]
     ptrs = _lib.ptr_array([h.data_ptr() for h in hs])
     with torch.cuda.device(dev):
+        t0 = timers.start()
         check(lib.grasp_bi_chain(ptrs, n, rows, d, d, _DTYPES[hs[0].dtype], float(scale), acc.data_ptr(), _stream()),
               "grasp_bi_chain")
+        timers.stop("grasp_bi_chain", t0, bytes_=2.0 * (n - 1) * rows * d * hs[0].element_size())
 
 
 # -------------------------------------------------------------------------- SVD
@@ -148,11 +195,15 @@ def svd_batched(mats: Sequence[torch.Tensor], prec: Optional[int] = None, max_sw
         raise GraspLibraryError("grasp_svd_workspace_bytes rejected the shapes")
     ws = _workspace(nbytes, dev)
     with torch.cuda.device(dev):
+        t0 = timers.start()
         check(lib.grasp_svd_batched(len(As), _lib.ptr_array([a.data_ptr() for a in As]), m_a, n_a, _lib.i64_array(n),
                                     _lib.ptr_array([u.data_ptr() for u in Us]),
                                     _lib.ptr_array([s.data_ptr() for s in Ss]),
                                     _lib.ptr_array([v.data_ptr() for v in Vs]), info.data_ptr(), _prec(prec),
                                     int(max_sweeps), ws.data_ptr(), ws.numel(), _stream()), "grasp_svd_batched")
+        timers.stop("grasp_svd_batched", t0,
+                    flops=sum(8.0 * max(a, b) * min(a, b) ** 2 + 4.0 / 3.0 * min(a, b) ** 3 for a, b in zip(m, n)),
+                    mma_per_flop=0.0)
     # keep the workspace alive until the stream has consumed it
     ws.record_stream(torch.cuda.current_stream())
     out = list(zip(Us, Ss, Vs))
@@ -196,10 +247,12 @@ def sigma_score(U: torch.Tensor, G: torch.Tensor, Vh: torch.Tensor, S: Optional[
     p = _prec(prec)
     ws = _workspace(lib.grasp_sigma_score_workspace_bytes(out, in_, r, p), dev)
     with torch.cuda.device(dev):
+        t0 = timers.start()
         check(lib.grasp_sigma_score(U.data_ptr(), G.data_ptr(), Vh.data_ptr(), S.data_ptr() if S is not None else None,
                                     out, in_, r, _metric(metric), int(accumulate), dsigma.data_ptr(),
                                     score.data_ptr() if score is not None else None, p, ws.data_ptr(), ws.numel(),
                                     _stream()), "grasp_sigma_score")
+        timers.stop("grasp_sigma_score", t0, flops=2.0 * r * out * in_ + 2.0 * r * in_, mma_per_flop=_mma_per_flop(p))
     ws.record_stream(torch.cuda.current_stream())
     return dsigma, score
 
@@ -276,9 +329,12 @@ def lowrank_rebuild(U: torch.Tensor, S: torch.Tensor, Vh: torch.Tensor, idx: tor
     p = _prec(prec)
     ws = _workspace(lib.grasp_lowrank_rebuild_workspace_bytes(out, in_, k, p), dev)
     with torch.cuda.device(dev):
+        t0 = timers.start()
         check(lib.grasp_lowrank_rebuild(U.data_ptr(), S.data_ptr(), Vh.data_ptr(), idx.data_ptr(), k, out, in_, r,
                                         _DTYPES[out_dtype], W.data_ptr(), p, ws.data_ptr(), ws.numel(), _stream()),
               "grasp_lowrank_rebuild")
+        timers.stop("grasp_lowrank_rebuild", t0, flops=2.0 * out * in_ * k,
+                    bytes_=4.0 * k * (out + in_) + W.element_size() * out * in_, mma_per_flop=_mma_per_flop(p))
     ws.record_stream(torch.cuda.current_stream())
     return W
 
@@ -322,8 +378,10 @@ def gemm(A: torch.Tensor, B: torch.Tensor, ta: bool = False, tb: bool = False, a
     p = _prec(prec)
     ws = _workspace(lib.grasp_gemm_workspace_bytes(M, N, K, p), dev)
     with torch.cuda.device(dev):
+        t0 = timers.start()
         check(lib.grasp_gemm_f32(int(ta), int(tb), M, N, K, float(alpha), A.data_ptr(), A.shape[1], B.data_ptr(),
                                  B.shape[1], float(beta), C_out.data_ptr(), N, p, ws.data_ptr(), ws.numel(),
                                  _stream()), "grasp_gemm_f32")
+        timers.stop("grasp_gemm_f32", t0, flops=2.0 * M * N * K, mma_per_flop=_mma_per_flop(p))
     ws.record_stream(torch.cuda.current_stream())
     return C_out

@@ -80,7 +80,7 @@ int grasp_bi_chain(const void* const* hiddens, int n_states, int64_t rows, int64
  * U[i] [m, r] (ld r), S[i] [r] descending, Vh[i] [r, n] (ld n), r = min(m,n).
  * info (device int32 [4*batch]): {sweeps used, converged(0/1),
  * float bits of the last sweep's max relative off-diagonal, reserved}.
- * prec: GRASP_PREC_*; max_sweeps <= 0 selects the default (24).
+ * prec: GRASP_PREC_*; max_sweeps <= 0 selects the default (32).
  * All shape arrays are HOST arrays; A/U/S/Vh are HOST arrays of device ptrs.
  * ------------------------------------------------------------------------- */
 size_t grasp_svd_workspace_bytes(int batch, const int64_t* m, const int64_t* n);

@@ -151,7 +151,7 @@ def test_svd_batched_mixed_shapes_and_info(cuda):
         check_svd(A, U, S, Vh, restate.svd(A)[1])
     info = info.cpu()
     assert torch.all(info[:, 1] == 1), f"not converged: {info}"
-    assert torch.all(info[:, 0] <= 20)
+    assert torch.all(info[:, 0] <= 24)
 
 
 def test_svd_edge_cases(cuda):
