@@ -324,6 +324,8 @@ def run_ours(a):
                 "config": {"workload": workload_name(a), "micro_batch": a.micro_batch,
                            "l2": "inputs larger than L2 (27 GB of weights, 4.3 GB activation cache per layer)",
                            "warmup_samples": min(a.warmup_samples, a.samples), "layers_chosen": gm.redundant_layers,
+                           "kept_index_checksum": int(sum(int(v.sum()) * (i + 1) for i, v in
+                                                          enumerate(kept[n] for n in sorted(kept)))),
                            "stages_ms": {k: round(v, 2) for k, v in stages.items()}, "end_to_end_s": total_ms / 1e3},
                 "e2e": {"value": n_mat / (total_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d // a.steps,
                         "d2h_bytes_per_step": d2h // a.steps},

@@ -229,6 +229,11 @@ if __name__ == "__main__":
     except ImportError:
         pass
     args = parse_args()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and args.device == "cuda":
+        # torchrun: one process per GPU; the hot path shards matrices and calibration samples over the ranks
+        import torch.distributed as td
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        td.init_process_group("nccl")
     from transformers import AutoTokenizer
     tokenizer = AutoTokenizer.from_pretrained(args.model_name_or_path)
     tokenizer.pad_token = tokenizer.eos_token

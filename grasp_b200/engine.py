@@ -273,6 +273,8 @@ class LlamaRunner:
         self.use_grasp_gemm = use_grasp_gemm
         self.cache = {}          # layer id -> [n_samples, S, d] input of that layer
         self.cache_key = None    # id of the CalibrationSet the cache belongs to
+        self.ckpt = {}           # activation checkpoints written by the scoring pass
+        self.ckpt_key = None
 
     @staticmethod
     def supports(hf_model) -> bool:
@@ -322,8 +324,9 @@ class LlamaRunner:
     # ---- prefix cache -------------------------------------------------------------
     def invalidate_above(self, layer_id: int):
         """Layer `layer_id` changed: cached inputs of deeper layers are stale."""
-        for k in [k for k in self.cache if k > layer_id]:
-            del self.cache[k]
+        for store in (self.cache, self.ckpt):
+            for k in [k for k in store if k > layer_id]:
+                del store[k]
 
     def build_cache(self, calib: CalibrationSet, layer_ids):
         if self.cache_key != id(calib):
@@ -332,12 +335,19 @@ class LlamaRunner:
         if not need:
             return
         n = len(calib)
+        # start from the deepest activation checkpoint left by the layer-scoring pass (if any)
+        ckpt = self.ckpt if self.ckpt_key == id(calib) else {}
+        starts = [c for c in ckpt if c <= need[0]]
+        start = max(starts) if starts else None
         with torch.no_grad(), grasp_linear(self.use_grasp_gemm):
             for s in range(0, n, self.micro_batch):
                 ids = calib.input_ids[s:s + self.micro_batch]
-                hidden = self.embed(ids)
+                if start is None:
+                    hidden, first = self.embed(ids), 0
+                else:
+                    hidden, first = ckpt[start][s:s + ids.shape[0]], start
                 position_ids, pos_emb = self._pos(hidden)
-                for i in range(0, need[-1] + 1):
+                for i in range(first, need[-1] + 1):
                     if i in need:
                         if i not in self.cache:
                             self.cache[i] = torch.empty((n,) + tuple(hidden.shape[1:]), dtype=hidden.dtype,
@@ -345,13 +355,36 @@ class LlamaRunner:
                         self.cache[i][s:s + ids.shape[0]] = hidden
                     if i < need[-1]:
                         hidden = self._layer(i, hidden, position_ids, pos_emb)
+        self.ckpt, self.ckpt_key = {}, None      # checkpoints served their purpose: release the memory
+
+    def _plan_checkpoints(self, calib: CalibrationSet, hidden_shape, element_size):
+        """Layers whose input is kept during the scoring pass: as many evenly spaced ones as fit in a
+        third of the free device memory (the selected layers are unknown until scoring has finished)."""
+        if not calib.input_ids.is_cuda:
+            return []
+        per = len(calib) * hidden_shape[1] * hidden_shape[2] * element_size
+        free, _ = torch.cuda.mem_get_info(calib.input_ids.device)
+        count = int(min(self.n_layers - 1, (free // 3) // max(per, 1)))
+        if count <= 0:
+            return []
+        stride = -(-self.n_layers // (count + 1))
+        return list(range(stride, self.n_layers, stride))
 
     # ---- stage 1 ------------------------------------------------------------------
     def block_influence(self, calib: CalibrationSet, scorer: "BlockInfluence"):
+        self.ckpt, self.ckpt_key = {}, id(calib)
+        plan = None
         with torch.no_grad(), grasp_linear(self.use_grasp_gemm):
             for s in range(0, len(calib), self.micro_batch):
                 ids = calib.input_ids[s:s + self.micro_batch]
                 states = self.hidden_states(ids)
+                if plan is None:
+                    plan = self._plan_checkpoints(calib, states[0].shape, states[0].element_size())
+                    for l in plan:
+                        self.ckpt[l] = torch.empty((len(calib),) + tuple(states[0].shape[1:]), dtype=states[0].dtype,
+                                                   device=states[0].device)
+                for l in plan:
+                    self.ckpt[l][s:s + ids.shape[0]] = states[l]     # states[l] is the input of layer l
                 # the reference adds one mean per DataLoader batch: sum_s w_s * mean_t(sample s)
                 w = calib.weights[s:s + ids.shape[0]]
                 if bool((w == w[0]).all()):

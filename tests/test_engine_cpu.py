@@ -53,3 +53,19 @@ def test_layer_index_parsing():
     assert engine.layer_index("model.layers.17.mlp.down_proj") == 17
     assert engine.layer_index("layers.3.self_attn.q_proj") == 3
     assert engine.layer_index("lm_head") is None
+
+
+def test_cache_from_checkpoint_matches_cache_from_scratch():
+    model = synth.random_llama("tiny", seed=5)
+    runner = engine.LlamaRunner(model, micro_batch=2, use_grasp_gemm=False)
+    calib = engine.CalibrationSet(synth.calibration_dataloader(5, 12, 256, seed=3), "cpu")
+    with torch.no_grad():
+        states = runner.hidden_states(calib.input_ids)
+    runner.ckpt, runner.ckpt_key = {2: states[2].clone()}, id(calib)     # as left by the scoring pass
+    runner.build_cache(calib, [2, 3])
+    assert torch.allclose(runner.cache[2], states[2], atol=1e-6)
+    assert torch.allclose(runner.cache[3], states[3], atol=1e-5)
+    assert runner.ckpt == {}
+    runner.cache = {}
+    runner.build_cache(calib, [1])                                       # no usable checkpoint: from the embeddings
+    assert torch.allclose(runner.cache[1], states[1], atol=1e-5)
