@@ -18,6 +18,7 @@
 // the epilogue warps add the block result into fp32 registers with round-to-nearest.  The TMEM
 // buffers form a ring (512 / BN deep), so the MMA warp never waits for the epilogue.
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace grasp {
 
@@ -54,7 +55,9 @@ struct TcCfg {
   static_assert(BN == 128, "the epilogue keeps one accumulator row of BN floats in registers");
 };
 
-template <int NS, int BN, int EPI>
+// BMN = 1: the B planes are stored [plane][K][N] (N contiguous, i.e. op(B) as given when tb = 0) and are
+// fed to the tensor core as an MN-major operand: no transposing pre-pass.
+template <int NS, int BN, int EPI, int BMN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcParams p) {
   using Cfg = TcCfg<NS, BN>;
@@ -98,7 +101,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
           for (int pl = 0; pl < NS; ++pl) {
             tma_load_3d(sA + pl * TC_A_TILE, &mapA, &full_bar[stage], kb * TC_BK, m0, pl);
-            tma_load_3d(sB + pl * Cfg::B_TILE, &mapB, &full_bar[stage], kb * TC_BK, n0, pl);
+            if constexpr (BMN) {
+              // box = 64 n x 64 k; one box per 64-wide N chunk, chunks TC_BK*128 bytes apart
+#pragma unroll
+              for (int h = 0; h < BN / 64; ++h)
+                tma_load_3d(sB + pl * Cfg::B_TILE + h * (TC_BK * 128), &mapB, &full_bar[stage], n0 + h * 64,
+                            kb * TC_BK, pl);
+            } else {
+              tma_load_3d(sB + pl * Cfg::B_TILE, &mapB, &full_bar[stage], kb * TC_BK, n0, pl);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -107,7 +118,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, BN);
+      constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, BN, 0, BMN);
       // plane products, small terms first
       constexpr int NPROD = (NS == 2) ? 3 : 6;
       constexpr int PA[6] = {NS == 2 ? 1 : 2, NS == 2 ? 0 : 0, NS == 2 ? 0 : 1, 1, 0, 0};
@@ -125,11 +136,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
           for (int q = 0; q < NPROD; ++q) {
             const uint64_t da = umma_desc_kmajor_sw128(sA + PA[q] * TC_A_TILE);
-            const uint64_t db = umma_desc_kmajor_sw128(sB + PB[q] * Cfg::B_TILE);
+            const uint64_t db = BMN ? umma_desc_mnmajor_sw128(sB + PB[q] * Cfg::B_TILE, TC_BK * 128, 1024)
+                                    : umma_desc_kmajor_sw128(sB + PB[q] * Cfg::B_TILE);
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k) {
-              // +32 bytes per 16-element K step inside the 128-byte swizzle row
-              umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (q | k) != 0);
+              // K-major: +32 bytes per 16-element K step inside the 128-byte swizzle row;
+              // MN-major: 16 K rows = two 8-row groups = +2048 bytes
+              const uint64_t kb_step = BMN ? (uint64_t)(128 * k) : (uint64_t)(2 * k);
+              umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + kb_step, idesc, (q | k) != 0);
             }
           }
           umma_commit(&empty_bar[stage]);           // frees the smem stage when the MMAs retire
@@ -345,14 +359,31 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // planes [NS][R][Kp] bf16 -> 3-D map (k, r, plane), box 64 x box_rows x 1, 128-byte swizzle, zero OOB fill
-static int make_plane_map(CUtensorMap* map, const void* planes, int NS, int R, int K, int Kp, int box_rows) {
+static int make_plane_map(CUtensorMap* map, const void* planes, int NS, int R, int K, int Kp, int box_rows,
+                          int box_inner = TC_BK) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return -3; }
   cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)R, (cuuint64_t)NS};
   cuuint64_t strides[2] = {(cuuint64_t)Kp * 2, (cuuint64_t)R * Kp * 2};
-  cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(planes), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return -3; }
+  return 0;
+}
+
+// generic bf16 3-D map used by the SVD tensor-core kernels (declared in tc_common.cuh)
+int tc_make_map_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                   uint64_t stride2_bytes, uint32_t box0, uint32_t box1) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return -3; }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return -3; }
@@ -377,17 +408,20 @@ static int split_operand(const float* src, int64_t ld, int transposed, int R, in
   return 0;
 }
 
-template <int NS, int BN, int EPI>
+template <int NS, int BN, int EPI, int BMN = 0>
 static int launch_core(const __nv_bfloat16* Ap, const __nv_bfloat16* Bp, TcParams prm, void* stream) {
   using Cfg = TcCfg<NS, BN>;
   CUtensorMap mapA, mapB;
   int rc = make_plane_map(&mapA, Ap, NS, prm.M, prm.K, kp_of(prm.K), TC_BM);
   if (rc) return rc;
-  rc = make_plane_map(&mapB, Bp, NS, prm.N, prm.K, kp_of(prm.K), BN);
+  if (BMN)   // planes [NS][K][Np]: inner dimension N, rows K
+    rc = make_plane_map(&mapB, Bp, NS, prm.K, prm.N, kp_of(prm.N), TC_BK, 64);
+  else
+    rc = make_plane_map(&mapB, Bp, NS, prm.N, prm.K, kp_of(prm.K), BN);
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    rc = check_cuda(cudaFuncSetAttribute(tc_gemm_kernel<NS, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    rc = check_cuda(cudaFuncSetAttribute(tc_gemm_kernel<NS, BN, EPI, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES), "tc_gemm attr");
     if (rc) return rc;
     attr_set = true;
@@ -396,14 +430,21 @@ static int launch_core(const __nv_bfloat16* Ap, const __nv_bfloat16* Bp, TcParam
   prm.tiles_n = (int)ceil_div(prm.N, BN);
   const int total = prm.tiles_m * prm.tiles_n;
   const int grid = total < sm_count() ? total : sm_count();
-  GRASP_LAUNCH((tc_gemm_kernel<NS, BN, EPI>), dim3(grid), dim3(TC_THREADS), Cfg::SMEM_BYTES, stream, mapA, mapB, prm);
+  GRASP_LAUNCH((tc_gemm_kernel<NS, BN, EPI, BMN>), dim3(grid), dim3(TC_THREADS), Cfg::SMEM_BYTES, stream, mapA, mapB, prm);
   GRASP_CHECK_LAST("tc_gemm_kernel");
   return 0;
 }
 
+static bool use_bmn() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GRASP_GEMM_BMN"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
+
 size_t tc_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int prec) {
   const int NS = ns_of(prec);
-  return planes_bytes(NS, M, K) + planes_bytes(NS, N, K) + 2048;
+  const size_t b = planes_bytes(NS, N, K) > planes_bytes(NS, K, N) ? planes_bytes(NS, N, K) : planes_bytes(NS, K, N);
+  return planes_bytes(NS, M, K) + b + 2048;
 }
 
 size_t tc_sigma_workspace_bytes(int64_t out, int64_t in, int64_t r, int prec) {
@@ -426,16 +467,27 @@ int tc_gemm_f32(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, co
   int rc;
   // A: op(A) is M x K; stored [M][K] (ta=0, already K-major) or [K][M] (ta=1)
   // B: op(B) is K x N; K-major form is [N][K]: stored [N][K] when tb=1, [K][N] when tb=0 (needs the transpose)
+  // tb = 0: B is stored [K][N]; either transpose it in the split pre-pass (K-major operand) or keep it
+  // as it is and feed it as an MN-major operand (planes [K][Np])
+  const bool bmn = !tb && use_bmn();
   if (NS == 2) {
     rc = split_operand<2>(A, lda, ta, (int)M, (int)K, Ap, stream); if (rc) return rc;
-    rc = split_operand<2>(B, ldb, !tb, (int)N, (int)K, Bp, stream); if (rc) return rc;
+    rc = bmn ? split_operand<2>(B, ldb, 0, (int)K, (int)N, Bp, stream)
+             : split_operand<2>(B, ldb, !tb, (int)N, (int)K, Bp, stream);
+    if (rc) return rc;
   } else {
     rc = split_operand<3>(A, lda, ta, (int)M, (int)K, Ap, stream); if (rc) return rc;
-    rc = split_operand<3>(B, ldb, !tb, (int)N, (int)K, Bp, stream); if (rc) return rc;
+    rc = bmn ? split_operand<3>(B, ldb, 0, (int)K, (int)N, Bp, stream)
+             : split_operand<3>(B, ldb, !tb, (int)N, (int)K, Bp, stream);
+    if (rc) return rc;
   }
   TcParams prm{};
   prm.M = (int)M; prm.N = (int)N; prm.K = (int)K;
   prm.alpha = alpha; prm.beta = beta; prm.C = C; prm.ldc = ldc; prm.c_bf16 = c_bf16;
+  if (bmn) {
+    if (NS == 2) return launch_core<2, 128, EPI_STORE, 1>(Ap, Bp, prm, stream);
+    return launch_core<3, 128, EPI_STORE, 1>(Ap, Bp, prm, stream);
+  }
   if (NS == 2) return launch_core<2, 128, EPI_STORE>(Ap, Bp, prm, stream);
   return launch_core<3, 128, EPI_STORE>(Ap, Bp, prm, stream);
 }

@@ -15,9 +15,16 @@
 
 namespace grasp {
 
+// from gemm_tc.cu
+int tc_gemm_f32(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda,
+                const float* B, int64_t ldb, float beta, void* C, int64_t ldc, int c_bf16, int prec, void* ws,
+                size_t ws_bytes, void* stream);
+size_t tc_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int prec);
+
 constexpr int JB = 32;        // rows per block
 constexpr int JS = 2 * JB;    // rows per pair = order of the small eigenproblem
 constexpr int J_THREADS = 256;
+constexpr int EVD_THREADS = 1024;  // one 2x2 Gram block and two eigenvector items per thread and step
 constexpr int J_MAXMAT = 8;   // matrices per launch group
 constexpr int J_STATS = 64;   // uint32 slots of per-matrix status
 
@@ -25,6 +32,7 @@ struct SvdMat {
   float* Z;          // [rp][ldz]
   float* Gpart;      // [npairs][nsplit][JS*JS]
   float* ET;         // [npairs][JS*JS]
+  __nv_bfloat16* ETp;  // tensor-core path: [3][ntiles*128][128] block-diagonal ET planes (null on the CUDA-core path)
   int* pair_flag;    // [npairs] 1 = ET is not the identity
   uint32_t* stats;   // [J_STATS]: [0]=converged flag, [1]=sweeps used, [2]=last maxoff bits, [8+s]=maxoff bits of sweep s
 };
@@ -54,6 +62,10 @@ __device__ __forceinline__ const float* pair_row(const float* Z, int ldz, int I,
   const int row = (rr < JB) ? (I * JB + rr) : (J * JB + rr - JB);
   return Z + (int64_t)row * ldz;
 }
+
+}  // namespace grasp
+#include "svd_tc.cuh"
+namespace grasp {
 
 // ---------------------------------------------------------------------------
 // init: Z = [Y0 | I], zero padding.  trans: Y0[i][j] = A[j][i]
@@ -146,14 +158,15 @@ struct EvdSmem {
   float G[JS][JS + 1];
   double E[JS][JS + 1];
   double c[JS / 2], s[JS / 2];
-  int pp[JS / 2], qq[JS / 2];
+  float cf[JS / 2], sf[JS / 2];
   float red[32];
   int rank[JS];
+  int inv[JS];
   int rotated;
   int nonident;
 };
 
-__global__ void __launch_bounds__(J_THREADS)
+__global__ void __launch_bounds__(EVD_THREADS)
 svd_evd_kernel(SvdGroup g, int round, int sweep, float tol, int inner_cap) {
   const SvdMat& M = g.mat[blockIdx.y];
   if (M.stats[0]) return;
@@ -165,7 +178,7 @@ svd_evd_kernel(SvdGroup g, int round, int sweep, float tol, int inner_cap) {
 
   // G = sum of K-split partials (fixed order => deterministic)
   const float* gp = M.Gpart + (int64_t)pair * g.nsplit * (JS * JS);
-  for (int e = tid; e < JS * JS; e += J_THREADS) {
+  for (int e = tid; e < JS * JS; e += EVD_THREADS) {
     float v = 0.f;
     for (int sp = 0; sp < g.nsplit; ++sp) v += gp[(int64_t)sp * (JS * JS) + e];
     sm.G[e / JS][e % JS] = v;
@@ -175,7 +188,7 @@ svd_evd_kernel(SvdGroup g, int round, int sweep, float tol, int inner_cap) {
   __syncthreads();
   // symmetrise and measure the largest relative off-diagonal
   float maxoff = 0.f;
-  for (int e = tid; e < JS * JS; e += J_THREADS) {
+  for (int e = tid; e < JS * JS; e += EVD_THREADS) {
     const int i = e / JS, j = e % JS;
     if (i < j) {
       const float v = 0.5f * (sm.G[i][j] + sm.G[j][i]);
@@ -189,7 +202,7 @@ svd_evd_kernel(SvdGroup g, int round, int sweep, float tol, int inner_cap) {
   if ((tid & 31) == 0) sm.red[tid >> 5] = maxoff;
   __syncthreads();
   if (tid < 32) {
-    float v = (tid < J_THREADS / 32) ? sm.red[tid] : 0.f;
+    float v = sm.red[tid];
     v = warp_max(v);
     if (tid == 0) {
       sm.red[0] = v;
@@ -200,6 +213,8 @@ svd_evd_kernel(SvdGroup g, int round, int sweep, float tol, int inner_cap) {
   maxoff = sm.red[0];
 
   if (maxoff >= tol) {
+    // static work assignment: thread -> one 2x2 block (k1,k2) of G and two (row, pair) items of E
+    const int k1 = tid / H, k2 = tid % H;
     for (int isw = 0; isw < inner_cap; ++isw) {
       if (tid == 0) sm.rotated = 0;
       __syncthreads();
@@ -209,14 +224,15 @@ svd_evd_kernel(SvdGroup g, int round, int sweep, float tol, int inner_cap) {
           rr_pair(JS, t, tid, p, q);
           const float gpp = sm.G[p][p], gqq = sm.G[q][q], gpq = sm.G[p][q];
           double c = 1.0, s = 0.0;
+          float c0 = 1.f, s0 = 0.f;
           if (gpq != 0.f && fabsf(gpq) > tol * sqrtf(fabsf(gpp * gqq))) {
             // the angle only steers convergence: fp32 is enough for it.  Orthogonality needs
             // c^2 + s^2 == 1 far below fp32 rounding, so the pair is renormalised in fp64
             // (first-order: 1/sqrt(1+d) = 1 - d/2 for d ~ 1e-7) without any fp64 div/sqrt.
             const float tau = (gqq - gpp) / (2.f * gpq);
             const float tt = copysignf(1.f, tau) / (fabsf(tau) + sqrtf(fmaf(tau, tau, 1.f)));
-            const float c0 = rsqrtf(fmaf(tt, tt, 1.f));
-            const float s0 = tt * c0;
+            c0 = rsqrtf(fmaf(tt, tt, 1.f));
+            s0 = tt * c0;
             const double cd = (double)c0, sd = (double)s0;
             const double corr = 1.0 - 0.5 * (cd * cd + sd * sd - 1.0);
             c = cd * corr;
@@ -224,34 +240,41 @@ svd_evd_kernel(SvdGroup g, int round, int sweep, float tol, int inner_cap) {
             sm.rotated = 1;
             sm.nonident = 1;
           }
-          sm.c[tid] = c; sm.s[tid] = s; sm.pp[tid] = p; sm.qq[tid] = q;
+          sm.c[tid] = c; sm.s[tid] = s; sm.cf[tid] = c0; sm.sf[tid] = s0;
         }
         __syncthreads();
-        // G <- J^T G J on disjoint 2x2 blocks
-        for (int blk = tid; blk < H * H; blk += J_THREADS) {
-          const int k1 = blk / H, k2 = blk % H;
-          const float s1 = (float)sm.s[k1], s2 = (float)sm.s[k2];
-          if (s1 == 0.f && s2 == 0.f) continue;
-          const float c1 = (float)sm.c[k1], c2 = (float)sm.c[k2];
-          const int p1 = sm.pp[k1], q1 = sm.qq[k1], p2 = sm.pp[k2], q2 = sm.qq[k2];
-          const float b00 = sm.G[p1][p2], b01 = sm.G[p1][q2], b10 = sm.G[q1][p2], b11 = sm.G[q1][q2];
-          const float t00 = c1 * b00 - s1 * b10, t01 = c1 * b01 - s1 * b11;
-          const float t10 = s1 * b00 + c1 * b10, t11 = s1 * b01 + c1 * b11;
-          float n00 = c2 * t00 - s2 * t01, n01 = s2 * t00 + c2 * t01;
-          float n10 = c2 * t10 - s2 * t11, n11 = s2 * t10 + c2 * t11;
-          if (k1 == k2) { n01 = 0.f; n10 = 0.f; }
-          sm.G[p1][p2] = n00; sm.G[p1][q2] = n01; sm.G[q1][p2] = n10; sm.G[q1][q2] = n11;
+        // G <- J^T G J on disjoint 2x2 blocks (one block per thread)
+        {
+          const float s1 = sm.sf[k1], s2 = sm.sf[k2];
+          if (s1 != 0.f || s2 != 0.f) {
+            const float c1 = sm.cf[k1], c2 = sm.cf[k2];
+            int p1, q1, p2, q2;
+            rr_pair(JS, t, k1, p1, q1);
+            rr_pair(JS, t, k2, p2, q2);
+            const float b00 = sm.G[p1][p2], b01 = sm.G[p1][q2], b10 = sm.G[q1][p2], b11 = sm.G[q1][q2];
+            const float t00 = c1 * b00 - s1 * b10, t01 = c1 * b01 - s1 * b11;
+            const float t10 = s1 * b00 + c1 * b10, t11 = s1 * b01 + c1 * b11;
+            float n00 = c2 * t00 - s2 * t01, n01 = s2 * t00 + c2 * t01;
+            float n10 = c2 * t10 - s2 * t11, n11 = s2 * t10 + c2 * t11;
+            if (k1 == k2) { n01 = 0.f; n10 = 0.f; }
+            sm.G[p1][p2] = n00; sm.G[p1][q2] = n01; sm.G[q1][p2] = n10; sm.G[q1][q2] = n11;
+          }
         }
-        // E <- E J (fp64)
-        for (int it = tid; it < JS * H; it += J_THREADS) {
-          const int k = it % H, i = it / H;
-          const double s = sm.s[k];
-          if (s == 0.0) continue;
-          const double c = sm.c[k];
-          const int p = sm.pp[k], q = sm.qq[k];
-          const double ep = sm.E[i][p], eq = sm.E[i][q];
-          sm.E[i][p] = c * ep - s * eq;
-          sm.E[i][q] = s * ep + c * eq;
+        // E <- E J (fp64): rows i = k1 and k1 + 32, pair k2
+        {
+          const double s = sm.s[k2];
+          if (s != 0.0) {
+            const double c = sm.c[k2];
+            int p, q;
+            rr_pair(JS, t, k2, p, q);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int i = k1 + h * H;
+              const double ep = sm.E[i][p], eq = sm.E[i][q];
+              sm.E[i][p] = c * ep - s * eq;
+              sm.E[i][q] = s * ep + c * eq;
+            }
+          }
         }
         __syncthreads();
       }
@@ -272,10 +295,30 @@ svd_evd_kernel(SvdGroup g, int round, int sweep, float tol, int inner_cap) {
     if (rk != tid) sm.nonident = 1;
   }
   __syncthreads();
+  if (tid < JS) sm.inv[sm.rank[tid]] = tid;
+  __syncthreads();
   if (tid == 0) M.pair_flag[pair] = sm.nonident;
+  if (M.ETp) {
+    // block-diagonal ET of the two pairs of a tile as three bf16 planes (always written, identity included)
+    const int ntiles = (g.npairs + 1) / 2;
+    const int64_t plane = (int64_t)ntiles * 128 * 128;
+    __nv_bfloat16* base = M.ETp + ((int64_t)(pair >> 1) * 128 + (pair & 1) * 64) * 128;
+    for (int e = tid; e < JS * 128; e += EVD_THREADS) {
+      const int rn = e >> 7, col = e & 127;
+      const int i = col - (pair & 1) * 64;          // component index inside this pair's 64 columns
+      float x = 0.f;
+      if (i >= 0 && i < JS) x = (float)sm.E[i][sm.inv[rn]];   // row rn of ET = eigenvector of rank rn
+#pragma unroll
+      for (int pl = 0; pl < 3; ++pl) {
+        const __nv_bfloat16 b = __float2bfloat16_rn(x);
+        base[pl * plane + (int64_t)rn * 128 + col] = b;
+        x -= __bfloat162float(b);
+      }
+    }
+  }
   if (sm.nonident) {
     float* et = M.ET + (int64_t)pair * (JS * JS);
-    for (int e = tid; e < JS * JS; e += J_THREADS) {
+    for (int e = tid; e < JS * JS; e += EVD_THREADS) {
       const int c = e / JS, i = e % JS;       // eigenvector c, component i
       et[sm.rank[c] * JS + i] = (float)sm.E[i][c];
     }
@@ -334,13 +377,13 @@ svd_update_kernel(SvdGroup g, int round) {
 }
 
 // one thread per matrix: close the sweep
-__global__ void svd_sweep_end_kernel(SvdGroup g, int sweep, float tol) {
+__global__ void svd_sweep_end_kernel(SvdGroup g, int sweep, float tol, int cleanup_idx) {
   const int m = threadIdx.x;
   if (m >= g.nmat) return;
   uint32_t* st = g.mat[m].stats;
   if (st[0]) return;
   const float off = __uint_as_float(st[8 + sweep]);
-  st[1] = sweep + 1;
+  st[1] = (cleanup_idx < 0) ? sweep + 1 : st[3] + cleanup_idx + 1;   // sweeps used so far
   st[2] = st[8 + sweep];
   if (off < tol) st[0] = 1;
 }
@@ -399,11 +442,19 @@ __global__ void svd_emit_cols_kernel(const float* __restrict__ Z, int ldz, int c
   }
 }
 
+__global__ void svd_reopen_kernel(SvdGroup g) {
+  if (threadIdx.x < g.nmat) {
+    uint32_t* st = g.mat[threadIdx.x].stats;
+    st[3] = st[1];   // sweeps of the tensor-core phase
+    st[0] = 0;
+  }
+}
+
 __global__ void svd_info_kernel(const uint32_t* __restrict__ stats, int32_t* __restrict__ info) {
   info[0] = (int32_t)stats[1];
   info[1] = (int32_t)stats[0];
   info[2] = (int32_t)stats[2];
-  info[3] = 0;
+  info[3] = (int32_t)stats[3];   // sweeps of the tensor-core phase (0 on the CUDA-core path)
 }
 
 // ---------------------------------------------------------------------------
@@ -412,8 +463,8 @@ __global__ void svd_info_kernel(const uint32_t* __restrict__ stats, int32_t* __r
 struct SvdPlan {
   int64_t m, n;        // A is m x n
   int trans;           // 1 when m > n (work on A^T)
-  int r, L, rp, Lp, ldz, p, npairs, nsplit;
-  size_t off_Z, off_G, off_ET, off_flag, off_stats, off_sigma, off_perm, bytes;
+  int r, L, rp, Lp, ldz, p, npairs, nsplit, ntiles;
+  size_t off_Z, off_G, off_ET, off_flag, off_stats, off_sigma, off_perm, off_Zp, off_ETp, off_T, off_gws, gws_bytes, bytes;
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -443,6 +494,17 @@ static SvdPlan make_plan(int64_t m, int64_t n) {
   P.off_stats = o; o = align_up(o + (size_t)J_STATS * 4, 256);
   P.off_sigma = o; o = align_up(o + (size_t)P.rp * 4, 256);
   P.off_perm = o;  o = align_up(o + (size_t)P.rp * 8, 256);
+  // tensor-core path: Z and the block-diagonal ET as three bf16 planes each
+  P.ntiles = (P.npairs + 1) / 2;
+  o = align_up(o, 1024);
+  P.off_Zp = o;    o = align_up(o + (size_t)3 * P.rp * P.ldz * 2, 1024);
+  P.off_ETp = o;   o = align_up(o + (size_t)3 * P.ntiles * 128 * 128 * 2, 1024);
+  // clean-up stage: T = QT QT^T and the workspace of its three GEMMs
+  P.off_T = o;     o = align_up(o + (size_t)P.rp * P.rp * 4, 1024);
+  size_t g1 = tc_gemm_workspace_bytes(P.rp, P.rp, P.rp, GRASP_PREC_BF16X6);
+  size_t g2 = tc_gemm_workspace_bytes(P.rp, P.L, P.r, GRASP_PREC_BF16X6);
+  P.gws_bytes = align_up(g1 > g2 ? g1 : g2, 1024);
+  P.off_gws = o;   o = align_up(o + P.gws_bytes, 1024);
   P.bytes = o;
   return P;
 }
@@ -471,7 +533,7 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
   if (prec != GRASP_PREC_SIMT && prec != GRASP_PREC_BF16X3 && prec != GRASP_PREC_BF16X6)
     return bad_arg("svd: prec");
   if (max_sweeps <= 0) max_sweeps = 32;
-  if (max_sweeps > J_STATS - 8) max_sweeps = J_STATS - 8;
+  if (max_sweeps > J_STATS - 16) max_sweeps = J_STATS - 16;   // 8 status words + 8 clean-up sweeps
   for (int i = 0; i < batch; ++i) {
     if (!A[i] || !U[i] || !S[i] || !Vh[i]) return bad_arg("svd: null matrix pointer");
     if (m[i] <= 0 || n[i] <= 0 || lda[i] < n[i]) return bad_arg("svd: m/n/lda");
@@ -495,6 +557,20 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
   if (const char* e = getenv("GRASP_SVD_TOL")) tol = (float)atof(e);
   if (const char* e = getenv("GRASP_SVD_INNER_CAP")) inner_cap = atoi(e);
   cudaStream_t st = (cudaStream_t)stream;
+  bool use_tc = (prec != GRASP_PREC_SIMT);
+  if (const char* e = getenv("GRASP_SVD_TC")) use_tc = atoi(e) != 0;
+  if (use_tc) {
+    static bool tc_attr = false;
+    if (!tc_attr) {
+      int rc = check_cuda(cudaFuncSetAttribute(jacobi_tc_kernel<JT_GRAM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               JtCfg<JT_GRAM>::SMEM_BYTES), "jacobi_tc gram attr");
+      if (rc) return rc;
+      rc = check_cuda(cudaFuncSetAttribute(jacobi_tc_kernel<JT_UPDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           JtCfg<JT_UPDATE>::SMEM_BYTES), "jacobi_tc update attr");
+      if (rc) return rc;
+      tc_attr = true;
+    }
+  }
 
   // plans + workspace carving
   SvdPlan* plans = new SvdPlan[batch];
@@ -526,6 +602,7 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
         M.ET = reinterpret_cast<float*>(base[i] + plans[i].off_ET);
         M.pair_flag = reinterpret_cast<int*>(base[i] + plans[i].off_flag);
         M.stats = reinterpret_cast<uint32_t*>(base[i] + plans[i].off_stats);
+        M.ETp = use_tc ? reinterpret_cast<__nv_bfloat16*>(base[i] + plans[i].off_ETp) : nullptr;
         done[i] = true;
       }
     }
@@ -544,15 +621,95 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
     rc = check_cuda(cudaGetLastError(), "svd_init_kernel");
     if (rc) break;
 
+    JtMaps* maps = nullptr;
+    JtParams jp{};
+    if (use_tc && g.p >= 2) {
+      maps = new JtMaps;
+      jp.nmat = g.nmat; jp.rp = g.rp; jp.Lp = g.Lp; jp.ldz = g.ldz; jp.p = g.p; jp.npairs = g.npairs;
+      jp.ntiles = P.ntiles; jp.nsplit = g.nsplit;
+      for (int j = 0; j < g.nmat && !rc; ++j) {
+        const SvdPlan& Q = plans[members[j]];
+        __nv_bfloat16* Zp = reinterpret_cast<__nv_bfloat16*>(base[members[j]] + Q.off_Zp);
+        jp.mat[j].Z = g.mat[j].Z; jp.mat[j].Zp = Zp; jp.mat[j].Gpart = g.mat[j].Gpart;
+        jp.mat[j].pair_flag = g.mat[j].pair_flag; jp.mat[j].stats = g.mat[j].stats;
+        const int64_t n4 = (int64_t)Q.rp * Q.ldz / 4;
+        GRASP_LAUNCH(jt_split_kernel, dim3((unsigned)ceil_div(n4, 256)), dim3(256), 0, st, g.mat[j].Z, n4,
+                     (int64_t)Q.rp * Q.ldz, Zp);
+        rc = check_cuda(cudaMemsetAsync(g.mat[j].ETp, 0, (size_t)3 * Q.ntiles * 128 * 128 * 2, st), "svd ETp memset");
+        if (rc) break;
+        rc = tc_make_map_3d(&maps->z[j], Zp, (uint64_t)Q.ldz, (uint64_t)Q.rp, 3, (uint64_t)Q.ldz * 2,
+                            (uint64_t)Q.rp * Q.ldz * 2, 64, 32);
+        if (rc) break;
+        rc = tc_make_map_3d(&maps->et[j], g.mat[j].ETp, 128, (uint64_t)Q.ntiles * 128, 3, 128 * 2,
+                            (uint64_t)Q.ntiles * 128 * 128 * 2, 64, 128);
+      }
+      for (int j = g.nmat; j < J_MAXMAT && !rc; ++j) { maps->z[j] = maps->z[0]; maps->et[j] = maps->et[0]; }
+      if (rc) { delete maps; break; }
+    }
     if (g.p >= 2) {
+      const int tc_grid_g = min(sm_count(), g.nmat * P.ntiles * g.nsplit);
+      const int tc_grid_u = min(sm_count(), g.nmat * P.ntiles * (g.ldz / 128));
       for (int sweep = 0; sweep < max_sweeps; ++sweep) {
         for (int round = 0; round < g.p - 1; ++round) {
-          GRASP_LAUNCH(svd_gram_kernel, dim3(g.nsplit, g.npairs, g.nmat), dim3(J_THREADS), 0, st, g, round);
-          GRASP_LAUNCH(svd_evd_kernel, dim3(g.npairs, g.nmat), dim3(J_THREADS), sizeof(EvdSmem), st, g, round,
+          if (use_tc) {
+            jp.round = round;
+            GRASP_LAUNCH(jacobi_tc_kernel<JT_GRAM>, dim3(tc_grid_g), dim3(JT_THREADS), JtCfg<JT_GRAM>::SMEM_BYTES, st,
+                         *maps, jp);
+          } else {
+            GRASP_LAUNCH(svd_gram_kernel, dim3(g.nsplit, g.npairs, g.nmat), dim3(J_THREADS), 0, st, g, round);
+          }
+          GRASP_LAUNCH(svd_evd_kernel, dim3(g.npairs, g.nmat), dim3(EVD_THREADS), sizeof(EvdSmem), st, g, round,
                        sweep, tol, inner_cap);
-          GRASP_LAUNCH(svd_update_kernel, dim3(g.ldz / UP_TN, g.npairs, g.nmat), dim3(J_THREADS), 0, st, g, round);
+          if (use_tc) {
+            GRASP_LAUNCH(jacobi_tc_kernel<JT_UPDATE>, dim3(tc_grid_u), dim3(JT_THREADS), JtCfg<JT_UPDATE>::SMEM_BYTES,
+                         st, *maps, jp);
+          } else {
+            GRASP_LAUNCH(svd_update_kernel, dim3(g.ldz / UP_TN, g.npairs, g.nmat), dim3(J_THREADS), 0, st, g, round);
+          }
         }
-        GRASP_LAUNCH(svd_sweep_end_kernel, dim3(1), dim3(32), 0, st, g, sweep, tol);
+        // tensor-core phase: stop once the Gram is diagonal to 1e-4 (its own drift is of that order anyway)
+        GRASP_LAUNCH(svd_sweep_end_kernel, dim3(1), dim3(32), 0, st, g, sweep, use_tc ? 1e-4f : tol, -1);
+      }
+      delete maps;
+      if (use_tc) {
+        // ---- clean-up.  The tensor-core accumulator truncates, so every update shrinks Z by ~1e-7:
+        // after thousands of updates QT is only orthogonal to ~3e-4 and Y has drifted from QT*Y0 by as
+        // much.  One Newton-Schulz step re-orthogonalises QT (error -> its square), Y is recomputed as
+        // QT*Y0, and a few CUDA-core (unbiased fp32) sweeps finish from an almost diagonal Gram.
+        for (int j = 0; j < g.nmat && !rc; ++j) {
+          const int i = members[j];
+          const SvdPlan& Q = plans[i];
+          float* Zm = g.mat[j].Z;
+          float* QT = Zm + Q.Lp;
+          float* T = reinterpret_cast<float*>(base[i] + Q.off_T);
+          void* gws = base[i] + Q.off_gws;
+          rc = tc_gemm_f32(0, 1, Q.rp, Q.rp, Q.rp, 1.f, QT, Q.ldz, QT, Q.ldz, 0.f, T, Q.rp, 0, GRASP_PREC_BF16X6, gws,
+                           Q.gws_bytes, stream);
+          if (rc) break;
+          rc = tc_gemm_f32(0, 0, Q.rp, Q.rp, Q.rp, -0.5f, T, Q.rp, QT, Q.ldz, 1.5f, QT, Q.ldz, 0, GRASP_PREC_BF16X6, gws,
+                           Q.gws_bytes, stream);
+          if (rc) break;
+          rc = tc_gemm_f32(0, Q.trans ? 1 : 0, Q.rp, Q.L, Q.r, 1.f, QT, Q.ldz, A[i], lda[i], 0.f, Zm, Q.ldz, 0,
+                           GRASP_PREC_BF16X6, gws, Q.gws_bytes, stream);
+          g.mat[j].ETp = nullptr;
+        }
+        if (rc) break;
+        GRASP_LAUNCH(svd_reopen_kernel, dim3(1), dim3(32), 0, st, g);
+        // after the re-orthogonalisation the Gram is diagonal to ~3e-4, so Jacobi's quadratic convergence
+        // needs two sweeps; the fp32 CUDA-core Gram has a noise floor of ~1e-6 at L = 4096, hence the
+        // looser stopping test (rotations still use `tol`)
+        const int extra = 3;
+        const float cleanup_conv = 3e-6f;
+        for (int s2 = 0; s2 < extra; ++s2) {
+          const int sweep = max_sweeps + s2;
+          for (int round = 0; round < g.p - 1; ++round) {
+            GRASP_LAUNCH(svd_gram_kernel, dim3(g.nsplit, g.npairs, g.nmat), dim3(J_THREADS), 0, st, g, round);
+            GRASP_LAUNCH(svd_evd_kernel, dim3(g.npairs, g.nmat), dim3(EVD_THREADS), sizeof(EvdSmem), st, g, round,
+                         sweep, tol, inner_cap);
+            GRASP_LAUNCH(svd_update_kernel, dim3(g.ldz / UP_TN, g.npairs, g.nmat), dim3(J_THREADS), 0, st, g, round);
+          }
+          GRASP_LAUNCH(svd_sweep_end_kernel, dim3(1), dim3(32), 0, st, g, sweep, cleanup_conv, s2);
+        }
       }
       rc = check_cuda(cudaGetLastError(), "svd sweep kernels");
       if (rc) break;

@@ -1,0 +1,288 @@
+// Tensor-core (tcgen05 + TMA) Gram and update steps of the block-Jacobi SVD.
+//
+// Alongside the fp32 working matrix Z the SVD keeps Z as three bf16 planes (hi, mid, lo:
+// Z = p0 + p1 + p2 to ~24 bits).  One CTA tile handles TWO block pairs = 4 chunks of 32 rows
+// (I1, J1, I2, J2), so every MMA is the validated 128 x 128 x 16 shape:
+//   gram  : G_tile = Yt Yt^T over a K range (A and B descriptors point at the same smem planes);
+//           the two 64 x 64 diagonal blocks are the pair Grams (K split over CTAs, partials summed
+//           by the eigen-solve kernel in a fixed order)
+//   update: Znew_tile[128, 128 cols] = blockdiag(ET1, ET2) * Zt[128 rows, 128 cols], the rows of Z
+//           enter as the MN-major B operand straight from the row-major planes; the epilogue writes
+//           the new rows as fp32 and as planes, in place.
+// Six plane products per K step (bf16x6), per-K-block TMEM accumulators added in fp32 registers
+// (see gemm_tc.cu for why).  Included by svd_jacobi.cu only.
+#pragma once
+#include "tc_common.cuh"
+
+namespace grasp {
+
+using namespace tc;
+
+constexpr int JT_THREADS = 192;
+constexpr int JT_PLANE_TILE = 128 * 64 * 2;   // 16 KiB: 128 rows (or 64 k-rows x 2 halves) x 64 bf16
+constexpr int JT_NACC = 4;
+
+struct JtMaps {
+  CUtensorMap z[J_MAXMAT];    // planes [3][rp][ldz], box 64 cols x 32 rows
+  CUtensorMap et[J_MAXMAT];   // planes [3][ntiles*128][128], box 64 k x 128 m
+};
+
+struct JtMat {
+  float* Z;                   // fp32 master [rp][ldz]
+  __nv_bfloat16* Zp;          // planes [3][rp][ldz]
+  float* Gpart;               // [npairs][nsplit][64*64]
+  const int* pair_flag;
+  const uint32_t* stats;
+};
+
+struct JtParams {
+  JtMat mat[J_MAXMAT];
+  int nmat, rp, Lp, ldz, p, npairs, ntiles, nsplit, round;
+};
+
+enum { JT_GRAM = 0, JT_UPDATE = 1 };
+
+template <int MODE>
+struct JtCfg {
+  static constexpr int STAGE_BYTES = (MODE == JT_GRAM ? 3 : 6) * JT_PLANE_TILE;
+  static constexpr int STAGES = (MODE == JT_GRAM) ? 4 : 2;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+// chunk c (0..3) of tile t -> first row of the 32-row block; pairs beyond npairs alias pair 0 of the tile
+__device__ __forceinline__ int jt_chunk_row(const JtParams& p, int tile, int c) {
+  int pair = tile * 2 + (c >> 1);
+  if (pair >= p.npairs) pair = tile * 2;
+  int I, J;
+  rr_pair(p.p, p.round, pair, I, J);
+  return ((c & 1) ? J : I) * JB;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(JT_THREADS, 1)
+jacobi_tc_kernel(const __grid_constant__ JtMaps maps, const JtParams p) {
+  using Cfg = JtCfg<MODE>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], acc_full[JT_NACC], acc_empty[JT_NACC];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kblocks_total = p.Lp / 64;
+  const int per_split = (kblocks_total + p.nsplit - 1) / p.nsplit;
+  const int ncol = p.ldz / 128;
+  const int per_mat = (MODE == JT_GRAM) ? p.ntiles * p.nsplit : p.ntiles * ncol;
+  const int total = p.nmat * per_mat;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < JT_NACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(&tmem_base_smem);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  // work item decode shared by the three roles (must be identical in all of them)
+  auto decode = [&](int w, int& m, int& tile, int& sub, int& kb0, int& kb1) -> bool {
+    m = w / per_mat;
+    const int r = w - m * per_mat;
+    if (MODE == JT_GRAM) {
+      tile = r / p.nsplit; sub = r - tile * p.nsplit;
+      kb0 = sub * per_split; kb1 = min(kblocks_total, kb0 + per_split);
+    } else {
+      tile = r / ncol; sub = r - tile * ncol;
+      kb0 = 0; kb1 = 2;
+    }
+    if (p.mat[m].stats[0]) return false;                      // matrix already converged
+    if (MODE == JT_UPDATE) {
+      const int f0 = p.mat[m].pair_flag[tile * 2];
+      const int f1 = (tile * 2 + 1 < p.npairs) ? p.mat[m].pair_flag[tile * 2 + 1] : 0;
+      if (!f0 && !f1) return false;                           // both rotations are the identity
+    }
+    return kb1 > kb0 || MODE == JT_GRAM;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        int m, tile, sub, kb0, kb1;
+        if (!decode(w, m, tile, sub, kb0, kb1)) continue;
+        const CUtensorMap* zmap = &maps.z[m];
+        int rows[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) rows[c] = jt_chunk_row(p, tile, c);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          if (MODE == JT_GRAM) {
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl)
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                tma_load_3d(st + pl * JT_PLANE_TILE + c * 4096, zmap, &full_bar[stage], kb * 64, rows[c], pl);
+          } else {
+            unsigned char* sB = st + 3 * JT_PLANE_TILE;
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl) {
+              // A: ET planes, 128 m x 64 k of K block kb
+              tma_load_3d(st + pl * JT_PLANE_TILE, &maps.et[m], &full_bar[stage], kb * 64, tile * 128, pl);
+              // B: rows of Z as K (two 32-row chunks per K block), 128 columns as two 64-wide halves
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc)
+                  tma_load_3d(sB + pl * JT_PLANE_TILE + h * 8192 + cc * 4096, zmap, &full_bar[stage],
+                              sub * 128 + h * 64, rows[kb * 2 + cc], pl);
+            }
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0, MODE == JT_UPDATE ? 1 : 0);
+      constexpr int PA[6] = {2, 0, 1, 1, 0, 0};
+      constexpr int PB[6] = {0, 2, 1, 0, 1, 0};
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        int m, tile, sub, kb0, kb1;
+        if (!decode(w, m, tile, sub, kb0, kb1)) continue;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
+          const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sB = (MODE == JT_GRAM) ? sA : sA + 3 * JT_PLANE_TILE;
+#pragma unroll
+          for (int q = 0; q < 6; ++q) {
+            const uint64_t da = umma_desc_kmajor_sw128(sA + PA[q] * JT_PLANE_TILE);
+            const uint64_t db = (MODE == JT_GRAM) ? umma_desc_kmajor_sw128(sB + PB[q] * JT_PLANE_TILE)
+                                                  : umma_desc_mnmajor_sw128(sB + PB[q] * JT_PLANE_TILE, 8192, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t bstep = (MODE == JT_GRAM) ? (uint64_t)(2 * k) : (uint64_t)(128 * k);
+              umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + bstep, idesc, (q | k) != 0);
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          umma_commit(&acc_full[acc]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++acc == JT_NACC) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int mrow = quad * 32 + lane;             // row of the 128-row tile owned by this thread
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      int m, tile, sub, kb0, kb1;
+      if (!decode(w, m, tile, sub, kb0, kb1)) continue;
+      float racc[128];
+#pragma unroll
+      for (int j = 0; j < 128; ++j) racc[j] = 0.f;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&acc_full[acc], acc_phase);
+        tc_fence_after_sync();
+        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 128);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float t[32];
+          tmem_ld_32x32(t_row + (uint32_t)(c * 32), t);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) racc[c * 32 + j] += t[j];
+        }
+        tc_fence_before_sync();
+        mbar_arrive(&acc_empty[acc]);
+        if (++acc == JT_NACC) { acc = 0; acc_phase ^= 1; }
+      }
+      const JtMat& M = p.mat[m];
+      const int pair = tile * 2 + (mrow >> 6);
+      if (pair >= p.npairs) continue;               // second half of an odd last tile
+      if (MODE == JT_GRAM) {
+        // keep the 64 x 64 diagonal block of this row's pair
+        float* out = M.Gpart + ((int64_t)pair * p.nsplit + sub) * (JS * JS) + (mrow & 63) * JS;
+        const int c0 = (mrow >> 6) * 64;
+#pragma unroll
+        for (int j = 0; j < 64; j += 4) {
+          float4 v;
+          if (c0 == 0) v = make_float4(racc[j], racc[j + 1], racc[j + 2], racc[j + 3]);
+          else v = make_float4(racc[64 + j], racc[65 + j], racc[66 + j], racc[67 + j]);
+          *reinterpret_cast<float4*>(out + j) = v;
+        }
+      } else {
+        const int row = jt_chunk_row(p, tile, mrow >> 5) + (mrow & 31);
+        const int64_t off = (int64_t)row * p.ldz + sub * 128;
+        float* zf = M.Z + off;
+#pragma unroll
+        for (int j = 0; j < 128; j += 4)
+          *reinterpret_cast<float4*>(zf + j) = make_float4(racc[j], racc[j + 1], racc[j + 2], racc[j + 3]);
+        const int64_t plane = (int64_t)p.rp * p.ldz;
+#pragma unroll
+        for (int j = 0; j < 128; j += 8) {
+          uint32_t w0[4], w1[4], w2[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x0 = racc[j + 2 * e], x1 = racc[j + 2 * e + 1];
+            const __nv_bfloat16 a0 = __float2bfloat16_rn(x0), b0 = __float2bfloat16_rn(x1);
+            x0 -= __bfloat162float(a0); x1 -= __bfloat162float(b0);
+            const __nv_bfloat16 a1 = __float2bfloat16_rn(x0), b1 = __float2bfloat16_rn(x1);
+            x0 -= __bfloat162float(a1); x1 -= __bfloat162float(b1);
+            const __nv_bfloat16 a2 = __float2bfloat16_rn(x0), b2 = __float2bfloat16_rn(x1);
+            w0[e] = (uint32_t)__bfloat16_as_ushort(a0) | ((uint32_t)__bfloat16_as_ushort(b0) << 16);
+            w1[e] = (uint32_t)__bfloat16_as_ushort(a1) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
+            w2[e] = (uint32_t)__bfloat16_as_ushort(a2) | ((uint32_t)__bfloat16_as_ushort(b2) << 16);
+          }
+          __nv_bfloat16* zp = M.Zp + off + j;
+          *reinterpret_cast<uint4*>(zp) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+          *reinterpret_cast<uint4*>(zp + plane) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+          *reinterpret_cast<uint4*>(zp + 2 * plane) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// fp32 Z -> three bf16 planes (whole working matrix, once after init)
+__global__ void jt_split_kernel(const float* __restrict__ Z, int64_t n4, int64_t plane, __nv_bfloat16* __restrict__ Zp) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = reinterpret_cast<const float4*>(Z)[i];
+  float x[4] = {v.x, v.y, v.z, v.w};
+  uint16_t h[3][4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+      const __nv_bfloat16 b = __float2bfloat16_rn(x[e]);
+      h[pl][e] = __bfloat16_as_ushort(b);
+      x[e] -= __bfloat162float(b);
+    }
+  }
+#pragma unroll
+  for (int pl = 0; pl < 3; ++pl) {
+    uint2 w;
+    w.x = (uint32_t)h[pl][0] | ((uint32_t)h[pl][1] << 16);
+    w.y = (uint32_t)h[pl][2] | ((uint32_t)h[pl][3] << 16);
+    reinterpret_cast<uint2*>(Zp + pl * plane)[i] = w;
+  }
+}
+
+}  // namespace grasp

@@ -127,14 +127,33 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                                // layout type: SWIZZLE_128B
   return d;
 }
-// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M x N tile
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
+// MN-major operand tile: rows are K, 64 MN-elements (128 bytes) per row, 128-byte swizzle.  8-row K
+// groups are `sbo` bytes apart, successive 64-wide MN chunks `lbo` bytes apart (canonical layout
+// ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO)) in elements, CUTLASS mma_sm100_desc.hpp).
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, M x N tile; *_mn = 1 selects an MN-major operand
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn = 0, uint32_t b_mn = 0) {
   return (1u << 4)            // D format: F32
          | (1u << 7)          // A format: BF16
          | (1u << 10)         // B format: BF16
+         | (a_mn << 15)       // A major
+         | (b_mn << 16)       // B major
          | ((N >> 3) << 17)   // N / 8
          | ((M >> 4) << 24);  // M / 16
 }
 
 }  // namespace tc
+
+// host: encode a bf16 3-D tiled tensor map with the 128-byte swizzle (gemm_tc.cu)
+int tc_make_map_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                   uint64_t stride2_bytes, uint32_t box0, uint32_t box1);
+
 }  // namespace grasp

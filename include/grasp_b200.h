@@ -79,7 +79,8 @@ int grasp_bi_chain(const void* const* hiddens, int n_states, int64_t rows, int64
  * modeling_grasp.py:231.  A[i] is m[i] x n[i] fp32 (lda[i]); outputs
  * U[i] [m, r] (ld r), S[i] [r] descending, Vh[i] [r, n] (ld n), r = min(m,n).
  * info (device int32 [4*batch]): {sweeps used, converged(0/1),
- * float bits of the last sweep's max relative off-diagonal, reserved}.
+ * float bits of the last sweep's max relative off-diagonal, sweeps of the
+ * tensor-core phase}.
  * prec: GRASP_PREC_*; max_sweeps <= 0 selects the default (32).
  * All shape arrays are HOST arrays; A/U/S/Vh are HOST arrays of device ptrs.
  * ------------------------------------------------------------------------- */
