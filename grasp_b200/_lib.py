@@ -8,7 +8,7 @@ from pathlib import Path
 _LIB = None
 _LIB_PATH = Path(__file__).resolve().parent / "libgrasp_b200.so"
 
-PREC_SIMT, PREC_BF16X3, PREC_BF16X6 = 0, 3, 6
+PREC_SIMT, PREC_BF16X3, PREC_BF16X6, PREC_F16X3 = 0, 3, 6, 16
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 METRIC_GRADIENT, METRIC_TAYLOR = 0, 1
 

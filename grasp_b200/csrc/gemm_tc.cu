@@ -41,6 +41,8 @@ struct TcParams {
   const float* Umul;  // EPI_SIGMA: [M][ldu], multiplied element-wise before the column reduction
   int64_t ldu;
   float* partial;     // EPI_SIGMA: [tiles_m][N]
+  const float* inv_sa;  // F16 planes: per-row inverse scale of A (M) and B (N); the accumulator is
+  const float* inv_sb;  //   multiplied by inv_sa[m] * inv_sb[n] before the epilogue
 };
 
 template <int NS, int BN>
@@ -57,7 +59,8 @@ struct TcCfg {
 
 // BMN = 1: the B planes are stored [plane][K][N] (N contiguous, i.e. op(B) as given when tb = 0) and are
 // fed to the tensor core as an MN-major operand: no transposing pre-pass.
-template <int NS, int BN, int EPI, int BMN>
+// F16 = 1: the planes hold fp16 (hi, lo) of row-scaled operands (2 planes, 3 products, ~3e-7).
+template <int NS, int BN, int EPI, int BMN, int F16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcParams p) {
   using Cfg = TcCfg<NS, BN>;
@@ -118,7 +121,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, BN, 0, BMN);
+      constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, BN, 0, BMN, F16);
       // plane products, small terms first
       constexpr int NPROD = (NS == 2) ? 3 : 6;
       constexpr int PA[6] = {NS == 2 ? 1 : 2, NS == 2 ? 0 : 0, NS == 2 ? 0 : 1, 1, 0, 0};
@@ -180,6 +183,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         tc_fence_before_sync();
         mbar_arrive(&acc_empty[acc]);               // hand the TMEM buffer back to the MMA warp
         if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+      }
+      if constexpr (F16) {
+        // undo the per-row power-of-two scaling of the fp16 planes (exact)
+        const float ia = (row < p.M) ? p.inv_sa[row] : 0.f;
+#pragma unroll
+        for (int j = 0; j < BN; ++j) racc[j] *= ia * ((n0 + j < p.N) ? __ldg(p.inv_sb + n0 + j) : 0.f);
       }
 #pragma unroll
       for (int c = 0; c < BN / 32; ++c) {
@@ -340,6 +349,101 @@ __global__ void split_transposed_kernel(const float* __restrict__ src, int64_t l
 }
 
 // ---------------------------------------------------------------------------
+// fp16 planes: x*s = hi + lo with s a per-row power of two that puts the row maximum in [2^14, 2^15)
+// (fp16 keeps 11 bits, two planes 22; the row scale keeps every row inside fp16's range).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void scale_from_max(float m, float& s, float& inv) {
+  const int ef = (int)((__float_as_uint(m) >> 23) & 0xffu);     // biased exponent of the row maximum
+  if (ef == 0 || ef == 0xff) { s = 1.f; inv = 1.f; return; }    // zero / denormal / inf / nan row: leave as is
+  int e = 14 - (ef - 127);                                      // s = 2^e
+  e = e > 100 ? 100 : (e < -100 ? -100 : e);
+  s = __uint_as_float((uint32_t)(127 + e) << 23);
+  inv = __uint_as_float((uint32_t)(127 - e) << 23);
+}
+
+// scale[r], inv[r] from max_k |src[r*ld + k]|  (one warp per row)
+__global__ void rowmax_scale_kernel(const float* __restrict__ src, int64_t ld, int R, int K, float* __restrict__ scale,
+                                    float* __restrict__ inv) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const float* row = src + (int64_t)r * ld;
+  float m = 0.f;
+  for (int k = threadIdx.x & 31; k < K; k += 32) m = fmaxf(m, fabsf(row[k]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) scale_from_max(m, scale[r], inv[r]);
+}
+
+// scale[c], inv[c] from max_r |src[r*ld + c]|  (32 columns per block, coalesced rows)
+__global__ void colmax_scale_kernel(const float* __restrict__ src, int64_t ld, int R, int Ccols, float* __restrict__ scale,
+                                    float* __restrict__ inv) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float m = 0.f;
+  if (c < Ccols)
+    for (int r = threadIdx.y; r < R; r += 8) m = fmaxf(m, fabsf(src[(int64_t)r * ld + c]));
+  red[threadIdx.y][threadIdx.x] = m;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < Ccols) {
+#pragma unroll
+    for (int y = 1; y < 8; ++y) m = fmaxf(m, red[y][threadIdx.x]);
+    scale_from_max(m, scale[c], inv[c]);
+  }
+}
+
+__device__ __forceinline__ void split_f16(float x, uint16_t& hi, uint16_t& lo) {
+  const __half h = __float2half_rn(x);
+  const __half l = __float2half_rn(x - __half2float(h));
+  hi = __half_as_ushort(h);
+  lo = __half_as_ushort(l);
+}
+
+// planes[pl][r][k] = part_pl(src[r*ld + k] * rs[r] * cs[k]); rs / cs nullable (exactly one is used)
+__global__ void split_rows_f16_kernel(const float* __restrict__ src, int64_t ld, int R, int K, int Kp,
+                                      const float* __restrict__ rs, const float* __restrict__ cs,
+                                      uint16_t* __restrict__ planes) {
+  const int r = blockIdx.y;
+  const int k0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (k0 >= Kp) return;
+  const float* srow = src + (int64_t)r * ld + k0;
+  const float sr = rs ? rs[r] : 1.f;
+  uint16_t hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float x = (k0 + j < K) ? srow[j] * sr : 0.f;
+    if (cs && k0 + j < K) x *= cs[k0 + j];
+    split_f16(x, hi[j], lo[j]);
+  }
+  uint16_t* d = planes + (int64_t)r * Kp + k0;
+  uint2 w;
+  w.x = (uint32_t)hi[0] | ((uint32_t)hi[1] << 16); w.y = (uint32_t)hi[2] | ((uint32_t)hi[3] << 16);
+  *reinterpret_cast<uint2*>(d) = w;
+  w.x = (uint32_t)lo[0] | ((uint32_t)lo[1] << 16); w.y = (uint32_t)lo[2] | ((uint32_t)lo[3] << 16);
+  *reinterpret_cast<uint2*>(d + (int64_t)R * Kp) = w;
+}
+
+// planes[pl][r][k] = part_pl(src[k*ld + r] * rs[r])   (source holds the transpose)
+__global__ void split_transposed_f16_kernel(const float* __restrict__ src, int64_t ld, int R, int K, int Kp,
+                                            const float* __restrict__ rs, uint16_t* __restrict__ planes) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int dy = ty; dy < 32; dy += 8) {
+    const int k = k0 + dy, r = r0 + tx;
+    tile[dy][tx] = (k < K && r < R) ? src[(int64_t)k * ld + r] : 0.f;
+  }
+  __syncthreads();
+  for (int dy = ty; dy < 32; dy += 8) {
+    const int r = r0 + dy, k = k0 + tx;
+    if (r < R && k < Kp) {
+      uint16_t hi, lo;
+      split_f16(tile[tx][dy] * rs[r], hi, lo);
+      planes[(int64_t)r * Kp + k] = hi;
+      planes[((int64_t)R + r) * Kp + k] = lo;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -393,6 +497,7 @@ int tc_make_map_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1,
 static int kp_of(int64_t K) { return (int)round_up(K, 8); }
 static size_t planes_bytes(int NS, int64_t R, int64_t K) { return round_up((int64_t)NS * R * kp_of(K) * 2, 1024); }
 static int ns_of(int prec) { return prec == GRASP_PREC_BF16X6 ? 3 : 2; }
+static bool is_f16(int prec) { return prec == GRASP_PREC_F16X3; }
 
 template <int NS>
 static int split_operand(const float* src, int64_t ld, int transposed, int R, int K, __nv_bfloat16* planes, void* stream) {
@@ -408,7 +513,34 @@ static int split_operand(const float* src, int64_t ld, int transposed, int R, in
   return 0;
 }
 
-template <int NS, int BN, int EPI, int BMN = 0>
+// fp16 planes of an operand whose K-major form is [R][K]:
+//   layout 0: src is [R][K] (scales per row)          -> planes [R][Kp]
+//   layout 1: src is [K][R] (transposed split)        -> planes [R][Kp]
+//   layout 2: src is [K][R], kept as it is (MN-major) -> planes [K][Rp], scales per column
+static int split_operand_f16(const float* src, int64_t ld, int layout, int R, int K, __nv_bfloat16* planes,
+                             float* scale, float* inv, void* stream) {
+  uint16_t* pl = reinterpret_cast<uint16_t*>(planes);
+  if (layout == 0) {
+    const int Kp = kp_of(K);
+    GRASP_LAUNCH(rowmax_scale_kernel, dim3((unsigned)ceil_div(R, 8)), dim3(256), 0, stream, src, ld, R, K, scale, inv);
+    GRASP_LAUNCH(split_rows_f16_kernel, dim3((unsigned)ceil_div(Kp, 4 * 256), (unsigned)R), dim3(256), 0, stream, src,
+                 ld, R, K, Kp, (const float*)scale, (const float*)nullptr, pl);
+  } else if (layout == 1) {
+    const int Kp = kp_of(K);
+    GRASP_LAUNCH(colmax_scale_kernel, dim3((unsigned)ceil_div(R, 32)), dim3(32, 8), 0, stream, src, ld, K, R, scale, inv);
+    GRASP_LAUNCH(split_transposed_f16_kernel, dim3((unsigned)ceil_div(Kp, 32), (unsigned)ceil_div(R, 32)), dim3(32, 8),
+                 0, stream, src, ld, R, K, Kp, (const float*)scale, pl);
+  } else {
+    const int Rp = kp_of(R);
+    GRASP_LAUNCH(colmax_scale_kernel, dim3((unsigned)ceil_div(R, 32)), dim3(32, 8), 0, stream, src, ld, K, R, scale, inv);
+    GRASP_LAUNCH(split_rows_f16_kernel, dim3((unsigned)ceil_div(Rp, 4 * 256), (unsigned)K), dim3(256), 0, stream, src,
+                 ld, K, R, Rp, (const float*)nullptr, (const float*)scale, pl);
+  }
+  GRASP_CHECK_LAST("fp16 split kernels");
+  return 0;
+}
+
+template <int NS, int BN, int EPI, int BMN = 0, int F16 = 0>
 static int launch_core(const __nv_bfloat16* Ap, const __nv_bfloat16* Bp, TcParams prm, void* stream) {
   using Cfg = TcCfg<NS, BN>;
   CUtensorMap mapA, mapB;
@@ -421,7 +553,7 @@ static int launch_core(const __nv_bfloat16* Ap, const __nv_bfloat16* Bp, TcParam
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    rc = check_cuda(cudaFuncSetAttribute(tc_gemm_kernel<NS, BN, EPI, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    rc = check_cuda(cudaFuncSetAttribute(tc_gemm_kernel<NS, BN, EPI, BMN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES), "tc_gemm attr");
     if (rc) return rc;
     attr_set = true;
@@ -430,7 +562,7 @@ static int launch_core(const __nv_bfloat16* Ap, const __nv_bfloat16* Bp, TcParam
   prm.tiles_n = (int)ceil_div(prm.N, BN);
   const int total = prm.tiles_m * prm.tiles_n;
   const int grid = total < sm_count() ? total : sm_count();
-  GRASP_LAUNCH((tc_gemm_kernel<NS, BN, EPI, BMN>), dim3(grid), dim3(TC_THREADS), Cfg::SMEM_BYTES, stream, mapA, mapB, prm);
+  GRASP_LAUNCH((tc_gemm_kernel<NS, BN, EPI, BMN, F16>), dim3(grid), dim3(TC_THREADS), Cfg::SMEM_BYTES, stream, mapA, mapB, prm);
   GRASP_CHECK_LAST("tc_gemm_kernel");
   return 0;
 }
@@ -444,7 +576,7 @@ static bool use_bmn() {
 size_t tc_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int prec) {
   const int NS = ns_of(prec);
   const size_t b = planes_bytes(NS, N, K) > planes_bytes(NS, K, N) ? planes_bytes(NS, N, K) : planes_bytes(NS, K, N);
-  return planes_bytes(NS, M, K) + b + 2048;
+  return planes_bytes(NS, M, K) + b + 2048 + (size_t)round_up(2 * (M + N) * 4, 1024);
 }
 
 size_t tc_sigma_workspace_bytes(int64_t out, int64_t in, int64_t r, int prec) {
@@ -470,6 +602,21 @@ int tc_gemm_f32(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, co
   // tb = 0: B is stored [K][N]; either transpose it in the split pre-pass (K-major operand) or keep it
   // as it is and feed it as an MN-major operand (planes [K][Np])
   const bool bmn = !tb && use_bmn();
+  if (is_f16(prec)) {
+    const size_t bbytes = planes_bytes(NS, N, K) > planes_bytes(NS, K, N) ? planes_bytes(NS, N, K) : planes_bytes(NS, K, N);
+    float* sc = reinterpret_cast<float*>(w + planes_bytes(NS, M, K) + bbytes);   // scale_a[M] inv_a[M] scale_b[N] inv_b[N]
+    float* inv_a = sc + M;
+    float* sc_b = sc + 2 * M;
+    float* inv_b = sc_b + N;
+    rc = split_operand_f16(A, lda, ta ? 1 : 0, (int)M, (int)K, Ap, sc, inv_a, stream); if (rc) return rc;
+    rc = split_operand_f16(B, ldb, tb ? 0 : (bmn ? 2 : 1), (int)N, (int)K, Bp, sc_b, inv_b, stream); if (rc) return rc;
+    TcParams prm{};
+    prm.M = (int)M; prm.N = (int)N; prm.K = (int)K;
+    prm.alpha = alpha; prm.beta = beta; prm.C = C; prm.ldc = ldc; prm.c_bf16 = c_bf16;
+    prm.inv_sa = inv_a; prm.inv_sb = inv_b;
+    if (bmn) return launch_core<2, 128, EPI_STORE, 1, 1>(Ap, Bp, prm, stream);
+    return launch_core<2, 128, EPI_STORE, 0, 1>(Ap, Bp, prm, stream);
+  }
   if (NS == 2) {
     rc = split_operand<2>(A, lda, ta, (int)M, (int)K, Ap, stream); if (rc) return rc;
     rc = bmn ? split_operand<2>(B, ldb, 0, (int)K, (int)N, Bp, stream)
@@ -503,6 +650,23 @@ int tc_sigma_partials(const float* U, const float* G, const float* Vh, int64_t o
   __nv_bfloat16* Gp = reinterpret_cast<__nv_bfloat16*>(w);
   __nv_bfloat16* Vp = reinterpret_cast<__nv_bfloat16*>(w + planes_bytes(NS, out, in));
   int rc;
+  if (is_f16(prec)) {
+    float* sc = reinterpret_cast<float*>(w + planes_bytes(NS, out, in) +
+                                         (planes_bytes(NS, r, in) > planes_bytes(NS, in, r) ? planes_bytes(NS, r, in)
+                                                                                            : planes_bytes(NS, in, r)));
+    float* inv_a = sc + out;
+    float* sc_b = sc + 2 * out;
+    float* inv_b = sc_b + r;
+    rc = split_operand_f16(G, in, 0, (int)out, (int)in, Gp, sc, inv_a, stream); if (rc) return rc;
+    rc = split_operand_f16(Vh, in, 0, (int)r, (int)in, Vp, sc_b, inv_b, stream); if (rc) return rc;
+    TcParams prm{};
+    prm.M = (int)out; prm.N = (int)r; prm.K = (int)in;
+    prm.alpha = 1.f; prm.beta = 0.f;
+    prm.Umul = U; prm.ldu = r; prm.partial = partial;
+    prm.inv_sa = inv_a; prm.inv_sb = inv_b;
+    *n_partials = tiles_m;
+    return launch_core<2, 128, EPI_SIGMA, 0, 1>(Gp, Vp, prm, stream);
+  }
   if (NS == 2) {
     rc = split_operand<2>(G, in, 0, (int)out, (int)in, Gp, stream); if (rc) return rc;
     rc = split_operand<2>(Vh, in, 0, (int)r, (int)in, Vp, stream); if (rc) return rc;

@@ -124,6 +124,6 @@ extern "C" int grasp_gemm_f32(int ta, int tb, int64_t M, int64_t N, int64_t K, f
     g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta;
     return launch_gemm_simt(g, 1, stream);
   }
-  if (prec != GRASP_PREC_BF16X3 && prec != GRASP_PREC_BF16X6) return bad_arg("gemm: prec");
+  if (prec != GRASP_PREC_BF16X3 && prec != GRASP_PREC_BF16X6 && prec != GRASP_PREC_F16X3) return bad_arg("gemm: prec");
   return tc_gemm_f32(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 0, prec, ws, ws_bytes, stream);
 }

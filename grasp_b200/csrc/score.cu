@@ -116,7 +116,7 @@ extern "C" int grasp_sigma_score(const float* U, const float* G, const float* Vh
     dim3 grid((unsigned)ceil_div(r, SC_T), (unsigned)n_partials);
     GRASP_LAUNCH(sigma_partial_simt_kernel, grid, dim3(SC_THREADS), 0, stream, U, G, Vh, out, in, r, partial);
     GRASP_CHECK_LAST("sigma_partial_simt_kernel");
-  } else if (prec == GRASP_PREC_BF16X3 || prec == GRASP_PREC_BF16X6) {
+  } else if (prec == GRASP_PREC_BF16X3 || prec == GRASP_PREC_BF16X6 || prec == GRASP_PREC_F16X3) {
     int rc = tc_sigma_partials(U, G, Vh, out, in, r, prec, partial, &n_partials, ws, ws_bytes, stream);
     if (rc) return rc;
   } else {

@@ -530,7 +530,7 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
   if (batch < 0) return bad_arg("svd: batch");
   if (batch == 0) return 0;
   if (!A || !m || !n || !lda || !U || !S || !Vh || !ws) return bad_arg("svd: null");
-  if (prec != GRASP_PREC_SIMT && prec != GRASP_PREC_BF16X3 && prec != GRASP_PREC_BF16X6)
+  if (prec != GRASP_PREC_SIMT && prec != GRASP_PREC_BF16X3 && prec != GRASP_PREC_BF16X6 && prec != GRASP_PREC_F16X3)
     return bad_arg("svd: prec");
   if (max_sweeps <= 0) max_sweeps = 32;
   if (max_sweeps > J_STATS - 16) max_sweeps = J_STATS - 16;   // 8 status words + 8 clean-up sweeps

@@ -140,10 +140,11 @@ __device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, 
   return d;
 }
 // kind::f16 instruction descriptor: bf16 x bf16 -> fp32, M x N tile; *_mn = 1 selects an MN-major operand
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn = 0, uint32_t b_mn = 0) {
-  return (1u << 4)            // D format: F32
-         | (1u << 7)          // A format: BF16
-         | (1u << 10)         // B format: BF16
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn = 0, uint32_t b_mn = 0,
+                                                       uint32_t fp16 = 0) {
+  return (1u << 4)                    // D format: F32
+         | ((fp16 ? 0u : 1u) << 7)    // A format: BF16 (1) or F16 (0)
+         | ((fp16 ? 0u : 1u) << 10)   // B format
          | (a_mn << 15)       // A major
          | (b_mn << 16)       // B major
          | ((N >> 3) << 17)   // N / 8

@@ -13,15 +13,15 @@ import torch
 
 from . import _lib
 from ._lib import (DTYPE_BF16, DTYPE_F16, DTYPE_F32, METRIC_GRADIENT, METRIC_TAYLOR, PREC_BF16X3, PREC_BF16X6,
-                   PREC_SIMT, GraspLibraryError, check)
+                   PREC_F16X3, PREC_SIMT, GraspLibraryError, check)
 
 # arithmetic of the GEMM-shaped stages; see include/grasp_b200.h
-_DEFAULT_PREC = PREC_BF16X6
+_DEFAULT_PREC = PREC_F16X3
 
 
 def set_default_precision(prec: int) -> None:
     global _DEFAULT_PREC
-    if prec not in (PREC_SIMT, PREC_BF16X3, PREC_BF16X6):
+    if prec not in (PREC_SIMT, PREC_BF16X3, PREC_BF16X6, PREC_F16X3):
         raise ValueError(f"unknown precision {prec}")
     _DEFAULT_PREC = prec
 
@@ -112,7 +112,7 @@ timers = _Timers()
 
 
 def _mma_per_flop(prec: int) -> float:
-    return {PREC_SIMT: 0.0, PREC_BF16X3: 3.0, PREC_BF16X6: 6.0}[prec]
+    return {PREC_SIMT: 0.0, PREC_BF16X3: 3.0, PREC_BF16X6: 6.0, PREC_F16X3: 3.0}[prec]
 
 
 # --------------------------------------------------------------------------- BI

@@ -41,10 +41,13 @@ extern "C" {
  * bf16 planes (hi, mid, lo) and multiplied on tcgen05 with fp32 accumulation.
  *   GRASP_PREC_SIMT  : plain fp32 FMA on CUDA cores (validation path)
  *   GRASP_PREC_BF16X3: 2 planes, 3 MMAs  (rel. err ~4e-6)
- *   GRASP_PREC_BF16X6: 3 planes, 6 MMAs  (rel. err ~1e-7, fp32-class)          */
+ *   GRASP_PREC_BF16X6: 3 planes, 6 MMAs  (rel. err ~1e-7, fp32-class)
+ *   GRASP_PREC_F16X3 : 2 fp16 planes of row-scaled operands, 3 MMAs (rel. err ~3e-7, fp32-class
+ *                      for operands whose rows span < 2^14 in magnitude around their maximum)   */
 #define GRASP_PREC_SIMT   0
 #define GRASP_PREC_BF16X3 3
 #define GRASP_PREC_BF16X6 6
+#define GRASP_PREC_F16X3  16
 
 int         grasp_abi_version(void);
 const char* grasp_last_error(void);

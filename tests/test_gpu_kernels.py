@@ -224,17 +224,39 @@ def test_rebuild_and_pack_match_reference_fixture(cuda, golden):
         assert (torch.linalg.norm(W.cpu() - case["W"]) / torch.linalg.norm(case["W"])).item() < 1e-5
 
 
-def test_gemm_all_transposes(cuda):
+@pytest.mark.parametrize("prec,tol", [(0, 1e-5), (16, 2e-6), (6, 2e-6), (3, 5e-5)])
+def test_gemm_all_transposes(cuda, prec, tol):
+    """grasp_gemm_f32 in every arithmetic (CUDA cores, fp16x3, bf16x6, bf16x3) against fp64."""
     from grasp_b200 import ops
     g = torch.Generator().manual_seed(9)
-    for (M, N, K) in [(64, 64, 64), (130, 70, 33), (511, 300, 257)]:
+    for (M, N, K) in [(64, 64, 64), (130, 70, 33), (511, 300, 257), (1, 1, 1), (128, 384, 4096)]:
         for ta in (False, True):
             for tb in (False, True):
                 A = torch.randn((K, M) if ta else (M, K), generator=g)
                 B = torch.randn((N, K) if tb else (K, N), generator=g)
                 want = (A.T if ta else A).double() @ (B.T if tb else B).double()
-                got = ops.gemm(A.to(cuda), B.to(cuda), ta=ta, tb=tb)
-                assert rel(got, want) < 1e-5
+                got = ops.gemm(A.to(cuda), B.to(cuda), ta=ta, tb=tb, prec=prec)
+                err = (torch.linalg.norm(got.double().cpu() - want) / torch.linalg.norm(want)).item()
+                assert err < tol, (M, N, K, ta, tb, err)
                 C0 = torch.randn(M, N, generator=g)
-                got2 = ops.gemm(A.to(cuda), B.to(cuda), ta=ta, tb=tb, alpha=0.5, beta=2.0, C_out=C0.to(cuda))
-                assert rel(got2, 0.5 * want + 2.0 * C0.double()) < 1e-5
+                got2 = ops.gemm(A.to(cuda), B.to(cuda), ta=ta, tb=tb, alpha=0.5, beta=2.0, C_out=C0.to(cuda), prec=prec)
+                want2 = 0.5 * want + 2.0 * C0.double()
+                assert (torch.linalg.norm(got2.double().cpu() - want2) / torch.linalg.norm(want2)).item() < tol
+
+
+def test_gemm_fp16_planes_survive_badly_scaled_rows(cuda):
+    """Rows spanning 12 decades (gradients next to activations): the per-row power-of-two scaling keeps
+    every row inside fp16 range; error measured per element against |a_m| |b_n|."""
+    from grasp_b200 import ops
+    g = torch.Generator().manual_seed(10)
+    A = torch.randn(200, 333, generator=g) * torch.logspace(-9, 3, 200)[:, None]
+    B = torch.randn(150, 333, generator=g) * torch.logspace(-6, 2, 150)[:, None]
+    want = A.double() @ B.double().T
+    scale = A.double().norm(dim=1)[:, None] * B.double().norm(dim=1)[None, :]
+    for b_given_kn in (False, True):
+        Bd = B.T.contiguous().to(cuda) if b_given_kn else B.to(cuda)
+        got = ops.gemm(A.to(cuda), Bd, tb=not b_given_kn, prec=16)
+        assert torch.isfinite(got).all()
+        assert ((got.double().cpu() - want).abs() / scale).max().item() < 2e-6
+    Z = torch.zeros(64, 64, device=cuda)
+    assert torch.all(ops.gemm(Z, Z, prec=16) == 0)

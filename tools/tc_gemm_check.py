@@ -34,7 +34,7 @@ def diag(C, want, tag):
 ok = True
 shapes = [(128, 256, 64), (128, 128, 64), (128, 256, 128), (256, 512, 256), (200, 300, 100), (1000, 777, 333),
           (511, 4096, 4096)]
-for prec, tol in ((3, 3e-5), (6, 2e-6)):
+for prec, tol in ((16, 1.5e-6), (3, 3e-5), (6, 2e-6)):
     for (M, N, K) in shapes:
         for ta, tb in ((False, True), (False, False), (True, False), (True, True)):
             A = torch.randn((K, M) if ta else (M, K), device=dev)
@@ -66,6 +66,23 @@ for prec, tol in ((3, 3e-5), (6, 2e-6)):
         break
 
 if ok:
+    # rows with wildly different magnitudes (gradients ~1e-7, activations ~1e2): the row scaling of F16X3 must cope
+    for prec, tol in ((16, 2e-6), (6, 2e-6)):
+        M, N, K = 300, 500, 700
+        A = torch.randn(M, K, device=dev) * torch.logspace(-9, 3, M, device=dev)[:, None]
+        B = torch.randn(N, K, device=dev) * torch.logspace(-6, 2, N, device=dev)[:, None]
+        want = A.double() @ B.double().T
+        C = ops.gemm(A, B, tb=True, prec=prec)
+        rowcol = (A.double().norm(dim=1)[:, None] * B.double().norm(dim=1)[None, :])
+        e = ((C.double() - want).abs() / rowcol).max().item()
+        print(f"prec {prec} graded rows: max elementwise err / (|a_m||b_n|) {e:.3e} {'ok' if e < tol else 'FAIL'}", flush=True)
+        ok = ok and e < tol
+        Bt = B.T.contiguous()
+        C2 = ops.gemm(A, Bt, tb=False, prec=prec)
+        e2 = ((C2.double() - want).abs() / rowcol).max().item()
+        print(f"prec {prec} graded rows (B given [K,N]): {e2:.3e} {'ok' if e2 < tol else 'FAIL'}", flush=True)
+        ok = ok and e2 < tol
+if ok:
     # sigma score on the tensor cores vs fp64
     for (o, i) in [(512, 512), (1376, 512), (512, 1376), (4096, 4096)]:
         r = min(o, i)
@@ -73,7 +90,7 @@ if ok:
         Vh = torch.linalg.qr(torch.randn(i, r, device=dev))[0].T.contiguous()
         G = torch.randn(o, i, device=dev); S = torch.rand(r, device=dev)
         want = ((U.double().T @ G.double()) * Vh.double()).sum(-1)
-        for prec in (3, 6):
+        for prec in (16, 3, 6):
             g, sc = ops.sigma_score(U, G, Vh, S, prec=prec)
             e = ((g.double() - want).abs().max() / want.abs().max()).item()
             print(f"sigma_score prec {prec} {o}x{i}: max rel {e:.3e}", flush=True)
@@ -83,7 +100,7 @@ if ok:
     # timings
     for (M, N, K) in [(4096, 4096, 4096), (8192, 8192, 8192), (511, 11008, 4096)]:
         A = torch.randn(M, K, device=dev); B = torch.randn(N, K, device=dev)
-        for prec in (3, 6):
+        for prec in (16, 3, 6):
             t = timed(lambda: ops.gemm(A, B, tb=True, prec=prec))
             res[f"gemm_{M}x{N}x{K}_p{prec}_ms"] = t
             print(f"gemm {M}x{N}x{K} prec {prec}: {t:.3f} ms  {2*M*N*K/t/1e9:.1f} TF/s fp32-equivalent", flush=True)
@@ -91,7 +108,7 @@ if ok:
         print(f"torch fp32 matmul {M}x{N}x{K}: {t:.3f} ms {2*M*N*K/t/1e9:.1f} TF/s", flush=True)
     o = i = 4096
     U = torch.randn(o, o, device=dev); Vh = torch.randn(o, o, device=dev); G = torch.randn(o, o, device=dev); S = torch.rand(o, device=dev)
-    for prec in (0, 3, 6):
+    for prec in (0, 16, 3, 6):
         t = timed(lambda: ops.sigma_score(U, G, Vh, S, prec=prec))
         print(f"sigma_score 4096^2 prec {prec}: {t:.3f} ms  {2*o*o*o/t/1e9:.1f} TF/s", flush=True)
         res[f"sigma_4096_p{prec}_ms"] = t
