@@ -53,15 +53,17 @@ struct TcCfg {
   static constexpr int NACC = 512 / BN;       // ring of per-K-block accumulators in TMEM
   static constexpr int TMEM_COLS = 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 4 * BN * 4 /*sigma red*/ + 256;
+  static constexpr int EPI_THREADS = BN;      // 4 epilogue warps per 128 output columns (128 fp32 accumulators per thread)
+  static constexpr int THREADS = 64 + EPI_THREADS;
   static_assert(STAGES >= 2, "need at least a double-buffered ring");
-  static_assert(BN == 128, "the epilogue keeps one accumulator row of BN floats in registers");
+  static_assert(BN == 128 || BN == 256, "supported tile widths");
 };
 
 // BMN = 1: the B planes are stored [plane][K][N] (N contiguous, i.e. op(B) as given when tb = 0) and are
 // fed to the tensor core as an MN-major operand: no transposing pre-pass.
 // F16 = 1: the planes hold fp16 (hi, lo) of row-scaled operands (2 planes, 3 products, ~3e-7).
 template <int NS, int BN, int EPI, int BMN, int F16>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(64 + BN, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcParams p) {
   using Cfg = TcCfg<NS, BN>;
   constexpr int STAGES = Cfg::STAGES;
@@ -81,7 +83,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     prefetch_tmap(&mapA);
     prefetch_tmap(&mapB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < NACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
+    for (int a = 0; a < NACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], Cfg::EPI_THREADS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(&tmem_base_smem);
@@ -159,21 +161,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..5)
     const int quad = warp & 3;                      // TMEM lane quadrant this warp may access
-    const int ep_tid = (int)threadIdx.x - 64;       // 0..127
+    const int half = (warp - 2) >> 2;               // which 128-column half of the tile this warp drains
+    const int ep_tid = (int)threadIdx.x - 64;       // 0..EPI_THREADS-1
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_blk = tile % p.tiles_m, n_blk = tile / p.tiles_m;
       const int row = m_blk * TC_BM + quad * 32 + lane;
       const int n0 = n_blk * BN;
-      float racc[BN];
+      float racc[128];
 #pragma unroll
-      for (int j = 0; j < BN; ++j) racc[j] = 0.f;
+      for (int j = 0; j < 128; ++j) racc[j] = 0.f;
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(&acc_full[acc], acc_phase);
         tc_fence_after_sync();
-        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * 128);
 #pragma unroll
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = 0; c < 4; ++c) {
           float t[32];
           tmem_ld_32x32(t_row + (uint32_t)(c * 32), t);
           tmem_ld_wait();
@@ -188,12 +191,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // undo the per-row power-of-two scaling of the fp16 planes (exact)
         const float ia = (row < p.M) ? p.inv_sa[row] : 0.f;
 #pragma unroll
-        for (int j = 0; j < BN; ++j) racc[j] *= ia * ((n0 + j < p.N) ? __ldg(p.inv_sb + n0 + j) : 0.f);
+        for (int j = 0; j < 128; ++j) {
+          const int col = n0 + half * 128 + j;
+          racc[j] *= ia * ((col < p.N) ? __ldg(p.inv_sb + col) : 0.f);
+        }
       }
 #pragma unroll
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < 4; ++c) {
         float* v = &racc[c * 32];
-        const int col0 = n0 + c * 32;
+        const int col0 = n0 + half * 128 + c * 32;
         if constexpr (EPI == EPI_STORE) {
           if (row < p.M && col0 < p.N) {
             const int ncols = min(32, p.N - col0);
@@ -258,17 +264,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
             }
           }
-          red[quad * BN + c * 32 + lane] = v[0];
+          red[quad * BN + half * 128 + c * 32 + lane] = v[0];
         }
       }
       if constexpr (EPI == EPI_SIGMA) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int j = ep_tid; j < BN; j += 128) {
+        asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EPI_THREADS) : "memory");
+        for (int j = ep_tid; j < BN; j += Cfg::EPI_THREADS) {
           const int col = n0 + j;
           if (col < p.N)
             p.partial[(int64_t)m_blk * p.N + col] = (red[j] + red[BN + j]) + (red[2 * BN + j] + red[3 * BN + j]);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EPI_THREADS) : "memory");
       }
     }
   }
@@ -494,6 +500,21 @@ int tc_make_map_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1,
   return 0;
 }
 
+int tc_make_map_4d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
+                   uint64_t stride1_bytes, uint64_t stride2_bytes, uint64_t stride3_bytes, uint32_t box0, uint32_t box1) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return -3; }
+  cuuint64_t dims[4] = {d0, d1, d2, d3};
+  cuuint64_t strides[3] = {stride1_bytes, stride2_bytes, stride3_bytes};
+  cuuint32_t box[4] = {box0, box1, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(4d) failed with CUresult %d", (int)r); return -3; }
+  return 0;
+}
+
 static int kp_of(int64_t K) { return (int)round_up(K, 8); }
 static size_t planes_bytes(int NS, int64_t R, int64_t K) { return round_up((int64_t)NS * R * kp_of(K) * 2, 1024); }
 static int ns_of(int prec) { return prec == GRASP_PREC_BF16X6 ? 3 : 2; }
@@ -562,9 +583,25 @@ static int launch_core(const __nv_bfloat16* Ap, const __nv_bfloat16* Bp, TcParam
   prm.tiles_n = (int)ceil_div(prm.N, BN);
   const int total = prm.tiles_m * prm.tiles_n;
   const int grid = total < sm_count() ? total : sm_count();
-  GRASP_LAUNCH((tc_gemm_kernel<NS, BN, EPI, BMN, F16>), dim3(grid), dim3(TC_THREADS), Cfg::SMEM_BYTES, stream, mapA, mapB, prm);
+  GRASP_LAUNCH((tc_gemm_kernel<NS, BN, EPI, BMN, F16>), dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, mapA, mapB, prm);
   GRASP_CHECK_LAST("tc_gemm_kernel");
   return 0;
+}
+
+// Tile width of the two-plane arithmetics.  The kernel is persistent with static tile assignment, so
+// the cost is (waves of tiles over the SMs) x (time of one tile); a 256-wide tile does twice the work
+// of a 128-wide one in ~1.55x the time (fewer operand bytes per MMA).  GRASP_GEMM_BN forces a width.
+static bool wide_tiles(int64_t M, int64_t N) {
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("GRASP_GEMM_BN"); forced = e ? atoi(e) : 0; }
+  if (forced == 128) return false;
+  if (forced == 256) return N > 128;
+  if (N <= 128) return false;
+  const int64_t sms = sm_count();
+  const int64_t tm = ceil_div(M, TC_BM);
+  const double c128 = (double)ceil_div(tm * ceil_div(N, 128), sms);
+  const double c256 = (double)ceil_div(tm * ceil_div(N, 256), sms) * 1.55;
+  return c256 < c128;
 }
 
 static bool use_bmn() {
@@ -614,6 +651,10 @@ int tc_gemm_f32(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, co
     prm.M = (int)M; prm.N = (int)N; prm.K = (int)K;
     prm.alpha = alpha; prm.beta = beta; prm.C = C; prm.ldc = ldc; prm.c_bf16 = c_bf16;
     prm.inv_sa = inv_a; prm.inv_sb = inv_b;
+    if (wide_tiles(M, N)) {
+      if (bmn) return launch_core<2, 256, EPI_STORE, 1, 1>(Ap, Bp, prm, stream);
+      return launch_core<2, 256, EPI_STORE, 0, 1>(Ap, Bp, prm, stream);
+    }
     if (bmn) return launch_core<2, 128, EPI_STORE, 1, 1>(Ap, Bp, prm, stream);
     return launch_core<2, 128, EPI_STORE, 0, 1>(Ap, Bp, prm, stream);
   }
@@ -665,6 +706,7 @@ int tc_sigma_partials(const float* U, const float* G, const float* Vh, int64_t o
     prm.Umul = U; prm.ldu = r; prm.partial = partial;
     prm.inv_sa = inv_a; prm.inv_sb = inv_b;
     *n_partials = tiles_m;
+    if (wide_tiles(out, r)) return launch_core<2, 256, EPI_SIGMA, 0, 1>(Gp, Vp, prm, stream);
     return launch_core<2, 128, EPI_SIGMA, 0, 1>(Gp, Vp, prm, stream);
   }
   if (NS == 2) {

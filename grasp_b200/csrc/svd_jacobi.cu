@@ -630,14 +630,13 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
       for (int j = 0; j < g.nmat && !rc; ++j) {
         const SvdPlan& Q = plans[members[j]];
         __nv_bfloat16* Zp = reinterpret_cast<__nv_bfloat16*>(base[members[j]] + Q.off_Zp);
-        jp.mat[j].Z = g.mat[j].Z; jp.mat[j].Zp = Zp; jp.mat[j].Gpart = g.mat[j].Gpart;
+        jp.mat[j].Zp = Zp; jp.mat[j].Gpart = g.mat[j].Gpart;
         jp.mat[j].pair_flag = g.mat[j].pair_flag; jp.mat[j].stats = g.mat[j].stats;
         const int64_t n4 = (int64_t)Q.rp * Q.ldz / 4;
-        GRASP_LAUNCH(jt_split_kernel, dim3((unsigned)ceil_div(n4, 256)), dim3(256), 0, st, g.mat[j].Z, n4,
-                     (int64_t)Q.rp * Q.ldz, Zp);
+        GRASP_LAUNCH(jt_split_kernel, dim3((unsigned)ceil_div(n4, 256)), dim3(256), 0, st, g.mat[j].Z, Q.rp, Q.ldz, Zp);
         rc = check_cuda(cudaMemsetAsync(g.mat[j].ETp, 0, (size_t)3 * Q.ntiles * 128 * 128 * 2, st), "svd ETp memset");
         if (rc) break;
-        rc = tc_make_map_3d(&maps->z[j], Zp, (uint64_t)Q.ldz, (uint64_t)Q.rp, 3, (uint64_t)Q.ldz * 2,
+        rc = tc_make_map_4d(&maps->z[j], Zp, 128, (uint64_t)Q.rp, (uint64_t)Q.ldz / 128, 3, 256, (uint64_t)Q.rp * 256,
                             (uint64_t)Q.rp * Q.ldz * 2, 64, 32);
         if (rc) break;
         rc = tc_make_map_3d(&maps->et[j], g.mat[j].ETp, 128, (uint64_t)Q.ntiles * 128, 3, 128 * 2,
@@ -681,6 +680,9 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
           const SvdPlan& Q = plans[i];
           float* Zm = g.mat[j].Z;
           float* QT = Zm + Q.Lp;
+          const int64_t n4 = (int64_t)Q.rp * Q.ldz / 4;
+          GRASP_LAUNCH(jt_merge_kernel, dim3((unsigned)ceil_div(n4, 256)), dim3(256), 0, st,
+                       reinterpret_cast<const __nv_bfloat16*>(base[i] + Q.off_Zp), Q.rp, Q.ldz, Zm);
           float* T = reinterpret_cast<float*>(base[i] + Q.off_T);
           void* gws = base[i] + Q.off_gws;
           rc = tc_gemm_f32(0, 1, Q.rp, Q.rp, Q.rp, 1.f, QT, Q.ldz, QT, Q.ldz, 0.f, T, Q.rp, 0, GRASP_PREC_BF16X6, gws,

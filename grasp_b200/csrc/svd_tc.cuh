@@ -1,7 +1,9 @@
 // Tensor-core (tcgen05 + TMA) Gram and update steps of the block-Jacobi SVD.
 //
-// Alongside the fp32 working matrix Z the SVD keeps Z as three bf16 planes (hi, mid, lo:
-// Z = p0 + p1 + p2 to ~24 bits).  One CTA tile handles TWO block pairs = 4 chunks of 32 rows
+// During the tensor-core phase the working matrix Z lives as three bf16 planes (hi, mid, lo:
+// Z = p0 + p1 + p2 to ~24 bits) in a TILE-MAJOR layout  Zp[plane][column tile][row][128]: the
+// 32-row x 128-column chunk a CTA loads or stores is one contiguous 8 KiB run (row-major Z would give
+// 256-byte pieces 16-30 KB apart, which halves the achieved HBM bandwidth).  One CTA tile handles TWO block pairs = 4 chunks of 32 rows
 // (I1, J1, I2, J2), so every MMA is the validated 128 x 128 x 16 shape:
 //   gram  : G_tile = Yt Yt^T over a K range (A and B descriptors point at the same smem planes);
 //           the two 64 x 64 diagonal blocks are the pair Grams (K split over CTAs, partials summed
@@ -23,13 +25,12 @@ constexpr int JT_PLANE_TILE = 128 * 64 * 2;   // 16 KiB: 128 rows (or 64 k-rows 
 constexpr int JT_NACC = 4;
 
 struct JtMaps {
-  CUtensorMap z[J_MAXMAT];    // planes [3][rp][ldz], box 64 cols x 32 rows
+  CUtensorMap z[J_MAXMAT];    // planes [3][ldz/128][rp][128] (4-D), box 64 cols x 32 rows
   CUtensorMap et[J_MAXMAT];   // planes [3][ntiles*128][128], box 64 k x 128 m
 };
 
 struct JtMat {
-  float* Z;                   // fp32 master [rp][ldz]
-  __nv_bfloat16* Zp;          // planes [3][rp][ldz]
+  __nv_bfloat16* Zp;          // planes [3][ldz/128][rp][128]
   float* Gpart;               // [npairs][nsplit][64*64]
   const int* pair_flag;
   const uint32_t* stats;
@@ -125,7 +126,7 @@ jacobi_tc_kernel(const __grid_constant__ JtMaps maps, const JtParams p) {
             for (int pl = 0; pl < 3; ++pl)
 #pragma unroll
               for (int c = 0; c < 4; ++c)
-                tma_load_3d(st + pl * JT_PLANE_TILE + c * 4096, zmap, &full_bar[stage], kb * 64, rows[c], pl);
+                tma_load_4d(st + pl * JT_PLANE_TILE + c * 4096, zmap, &full_bar[stage], (kb & 1) * 64, rows[c], kb >> 1, pl);
           } else {
             unsigned char* sB = st + 3 * JT_PLANE_TILE;
 #pragma unroll
@@ -137,8 +138,8 @@ jacobi_tc_kernel(const __grid_constant__ JtMaps maps, const JtParams p) {
               for (int h = 0; h < 2; ++h)
 #pragma unroll
                 for (int cc = 0; cc < 2; ++cc)
-                  tma_load_3d(sB + pl * JT_PLANE_TILE + h * 8192 + cc * 4096, zmap, &full_bar[stage],
-                              sub * 128 + h * 64, rows[kb * 2 + cc], pl);
+                  tma_load_4d(sB + pl * JT_PLANE_TILE + h * 8192 + cc * 4096, zmap, &full_bar[stage], h * 64,
+                              rows[kb * 2 + cc], sub, pl);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -222,11 +223,7 @@ jacobi_tc_kernel(const __grid_constant__ JtMaps maps, const JtParams p) {
         }
       } else {
         const int row = jt_chunk_row(p, tile, mrow >> 5) + (mrow & 31);
-        const int64_t off = (int64_t)row * p.ldz + sub * 128;
-        float* zf = M.Z + off;
-#pragma unroll
-        for (int j = 0; j < 128; j += 4)
-          *reinterpret_cast<float4*>(zf + j) = make_float4(racc[j], racc[j + 1], racc[j + 2], racc[j + 3]);
+        const int64_t off = ((int64_t)sub * p.rp + row) * 128;          // [column tile][row][128]
         const int64_t plane = (int64_t)p.rp * p.ldz;
 #pragma unroll
         for (int j = 0; j < 128; j += 8) {
@@ -260,10 +257,12 @@ jacobi_tc_kernel(const __grid_constant__ JtMaps maps, const JtParams p) {
   }
 }
 
-// fp32 Z -> three bf16 planes (whole working matrix, once after init)
-__global__ void jt_split_kernel(const float* __restrict__ Z, int64_t n4, int64_t plane, __nv_bfloat16* __restrict__ Zp) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// fp32 Z [rp][ldz] -> three bf16 planes, tile-major [plane][ldz/128][rp][128] (once after init)
+__global__ void jt_split_kernel(const float* __restrict__ Z, int rp, int ldz, __nv_bfloat16* __restrict__ Zp) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // one float4 per thread
+  const int64_t n4 = (int64_t)rp * ldz / 4;
   if (i >= n4) return;
+  const int row = (int)(i / (ldz / 4)), col = (int)(i % (ldz / 4)) * 4;
   const float4 v = reinterpret_cast<const float4*>(Z)[i];
   float x[4] = {v.x, v.y, v.z, v.w};
   uint16_t h[3][4];
@@ -276,13 +275,33 @@ __global__ void jt_split_kernel(const float* __restrict__ Z, int64_t n4, int64_t
       x[e] -= __bfloat162float(b);
     }
   }
+  const int64_t plane = (int64_t)rp * ldz;
+  const int64_t dst = ((int64_t)(col >> 7) * rp + row) * 128 + (col & 127);
 #pragma unroll
   for (int pl = 0; pl < 3; ++pl) {
     uint2 w;
     w.x = (uint32_t)h[pl][0] | ((uint32_t)h[pl][1] << 16);
     w.y = (uint32_t)h[pl][2] | ((uint32_t)h[pl][3] << 16);
-    reinterpret_cast<uint2*>(Zp + pl * plane)[i] = w;
+    *reinterpret_cast<uint2*>(Zp + pl * plane + dst) = w;
   }
+}
+
+// planes -> fp32 Z (end of the tensor-core phase)
+__global__ void jt_merge_kernel(const __nv_bfloat16* __restrict__ Zp, int rp, int ldz, float* __restrict__ Z) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n4 = (int64_t)rp * ldz / 4;
+  if (i >= n4) return;
+  const int row = (int)(i / (ldz / 4)), col = (int)(i % (ldz / 4)) * 4;
+  const int64_t plane = (int64_t)rp * ldz;
+  const int64_t src = ((int64_t)(col >> 7) * rp + row) * 128 + (col & 127);
+  float x[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int pl = 2; pl >= 0; --pl) {     // small parts first
+    const uint2 w = *reinterpret_cast<const uint2*>(Zp + pl * plane + src);
+    x[0] += __uint_as_float(w.x << 16); x[1] += __uint_as_float(w.x & 0xffff0000u);
+    x[2] += __uint_as_float(w.y << 16); x[3] += __uint_as_float(w.y & 0xffff0000u);
+  }
+  reinterpret_cast<float4*>(Z)[i] = make_float4(x[0], x[1], x[2], x[3]);
 }
 
 }  // namespace grasp

@@ -65,6 +65,13 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
 // ---- tcgen05 ------------------------------------------------------------------
 template <uint32_t NCOLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {  // whole warp
@@ -156,5 +163,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, u
 // host: encode a bf16 3-D tiled tensor map with the 128-byte swizzle (gemm_tc.cu)
 int tc_make_map_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                    uint64_t stride2_bytes, uint32_t box0, uint32_t box1);
+int tc_make_map_4d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
+                   uint64_t stride1_bytes, uint64_t stride2_bytes, uint64_t stride3_bytes, uint32_t box0, uint32_t box1);
 
 }  // namespace grasp

@@ -14,6 +14,11 @@ gm.prepare_calibration(dl, [0])
 gm.compress_block(0, "attention", ["q_proj", "k_proj", "v_proj", "o_proj"], device=dev)
 gm.get_svdlayer_gradients(dl, dev)          # warm
 torch.cuda.synchronize()
+import time
+t0 = time.perf_counter()
+gm.get_svdlayer_gradients(dl, dev)
+torch.cuda.synchronize()
+print(f"wall time of one pass (16 samples, 4 layers): {(time.perf_counter() - t0) * 1e3:.1f} ms")
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     gm.get_svdlayer_gradients(dl, dev)
     torch.cuda.synchronize()
