@@ -154,10 +154,13 @@ svd_gram_kernel(SvdGroup g, int round) {
 // G (fp32) and E (fp64) live in shared memory; rotation parameters in fp64.
 // grid (npairs, nmat)
 // ---------------------------------------------------------------------------
+// ET = float: eigenvectors accumulated in fp32 (tensor-core phase: its drift is removed by the clean-up
+// stage anyway); ET = double: fp64 accumulation with fp64-renormalised rotations (CUDA-core sweeps).
+template <typename ET>
 struct EvdSmem {
   float G[JS][JS + 1];
-  double E[JS][JS + 1];
-  double c[JS / 2], s[JS / 2];
+  ET E[JS][JS + 1];
+  ET c[JS / 2], s[JS / 2];
   float cf[JS / 2], sf[JS / 2];
   float red[32];
   int rank[JS];
@@ -166,12 +169,19 @@ struct EvdSmem {
   int nonident;
 };
 
+// next pair of a fixed tournament slot k when the round advances by one (see rr_pair)
+__device__ __forceinline__ void rr_advance(int& x, int& y, int k) {
+  y = (y + 1 == JS - 1) ? 0 : y + 1;
+  if (k != 0) x = (x + 1 == JS - 1) ? 0 : x + 1;
+}
+
+template <typename ET>
 __global__ void __launch_bounds__(EVD_THREADS)
 svd_evd_kernel(SvdGroup g, int round, int sweep, float tol, int inner_cap) {
   const SvdMat& M = g.mat[blockIdx.y];
   if (M.stats[0]) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  EvdSmem& sm = *reinterpret_cast<EvdSmem*>(smem_raw);
+  EvdSmem<ET>& sm = *reinterpret_cast<EvdSmem<ET>*>(smem_raw);
   const int tid = threadIdx.x;
   const int pair = blockIdx.x;
   constexpr int H = JS / 2;
@@ -182,7 +192,7 @@ svd_evd_kernel(SvdGroup g, int round, int sweep, float tol, int inner_cap) {
     float v = 0.f;
     for (int sp = 0; sp < g.nsplit; ++sp) v += gp[(int64_t)sp * (JS * JS) + e];
     sm.G[e / JS][e % JS] = v;
-    sm.E[e / JS][e % JS] = (e / JS == e % JS) ? 1.0 : 0.0;
+    sm.E[e / JS][e % JS] = (e / JS == e % JS) ? (ET)1 : (ET)0;
   }
   if (tid == 0) { sm.rotated = 0; sm.nonident = 0; }
   __syncthreads();
@@ -218,25 +228,38 @@ svd_evd_kernel(SvdGroup g, int round, int sweep, float tol, int inner_cap) {
     for (int isw = 0; isw < inner_cap; ++isw) {
       if (tid == 0) sm.rotated = 0;
       __syncthreads();
+      // unordered pairs of slots k1 / k2 in round t, advanced incrementally: slot 0 is (JS-1, t),
+      // slot k is ((t+k) mod (JS-1), (t-k) mod (JS-1))
+      int x1 = (k1 == 0) ? JS - 1 : k1, y1 = (k1 == 0) ? 0 : (JS - 1 - k1);
+      int x2 = (k2 == 0) ? JS - 1 : k2, y2 = (k2 == 0) ? 0 : (JS - 1 - k2);
       for (int t = 0; t < JS - 1; ++t) {
-        if (tid < H) {
-          int p, q;
-          rr_pair(JS, t, tid, p, q);
-          const float gpp = sm.G[p][p], gqq = sm.G[q][q], gpq = sm.G[p][q];
-          double c = 1.0, s = 0.0;
+        const int p1 = min(x1, y1), q1 = max(x1, y1), p2 = min(x2, y2), q2 = max(x2, y2);
+        if (tid < H) {   // k1 == 0, k2 == tid: this thread's (p2, q2) is the pair of slot tid
+          const float gpp = sm.G[p2][p2], gqq = sm.G[q2][q2], gpq = sm.G[p2][q2];
+          ET c = 1, s = 0;
           float c0 = 1.f, s0 = 0.f;
-          if (gpq != 0.f && fabsf(gpq) > tol * sqrtf(fabsf(gpp * gqq))) {
-            // the angle only steers convergence: fp32 is enough for it.  Orthogonality needs
-            // c^2 + s^2 == 1 far below fp32 rounding, so the pair is renormalised in fp64
-            // (first-order: 1/sqrt(1+d) = 1 - d/2 for d ~ 1e-7) without any fp64 div/sqrt.
-            const float tau = (gqq - gpp) / (2.f * gpq);
-            const float tt = copysignf(1.f, tau) / (fabsf(tau) + sqrtf(fmaf(tau, tau, 1.f)));
+          if (gpq != 0.f && gpq * gpq > tol * tol * fabsf(gpp * gqq)) {
+            // the angle only steers convergence: fp32 is enough for it
+            const float d = gqq - gpp, x = 2.f * gpq;
+            const float tt = x / (d + copysignf(sqrtf(fmaf(d, d, x * x)), d));
             c0 = rsqrtf(fmaf(tt, tt, 1.f));
             s0 = tt * c0;
-            const double cd = (double)c0, sd = (double)s0;
-            const double corr = 1.0 - 0.5 * (cd * cd + sd * sd - 1.0);
-            c = cd * corr;
-            s = sd * corr;
+            if constexpr (sizeof(ET) == 8) {
+              // orthogonality needs c^2 + s^2 == 1 far below fp32 rounding: renormalise in fp64
+              // (first order: 1/sqrt(1+e) = 1 - e/2 for e ~ 1e-7), no fp64 divide / sqrt
+              const double cd = (double)c0, sd = (double)s0;
+              const double corr = 1.0 - 0.5 * (cd * cd + sd * sd - 1.0);
+              c = cd * corr;
+              s = sd * corr;
+            } else {
+              // rsqrtf is approximate and its error has a preferred sign; a correction factor 1 + h with
+              // h ~ 1e-7 is not representable in fp32, so add c0*h instead: h = (1 - c0^2 - s0^2) / 2 from two
+              // fused multiply-adds (the residual is then unbiased fp32 rounding)
+              const float h = -0.5f * fmaf(s0, s0, fmaf(c0, c0, -1.0f));
+              c0 = fmaf(c0, h, c0);
+              s0 = fmaf(s0, h, s0);
+              c = c0; s = s0;
+            }
             sm.rotated = 1;
             sm.nonident = 1;
           }
@@ -248,9 +271,6 @@ svd_evd_kernel(SvdGroup g, int round, int sweep, float tol, int inner_cap) {
           const float s1 = sm.sf[k1], s2 = sm.sf[k2];
           if (s1 != 0.f || s2 != 0.f) {
             const float c1 = sm.cf[k1], c2 = sm.cf[k2];
-            int p1, q1, p2, q2;
-            rr_pair(JS, t, k1, p1, q1);
-            rr_pair(JS, t, k2, p2, q2);
             const float b00 = sm.G[p1][p2], b01 = sm.G[p1][q2], b10 = sm.G[q1][p2], b11 = sm.G[q1][q2];
             const float t00 = c1 * b00 - s1 * b10, t01 = c1 * b01 - s1 * b11;
             const float t10 = s1 * b00 + c1 * b10, t11 = s1 * b01 + c1 * b11;
@@ -259,23 +279,20 @@ svd_evd_kernel(SvdGroup g, int round, int sweep, float tol, int inner_cap) {
             if (k1 == k2) { n01 = 0.f; n10 = 0.f; }
             sm.G[p1][p2] = n00; sm.G[p1][q2] = n01; sm.G[q1][p2] = n10; sm.G[q1][q2] = n11;
           }
-        }
-        // E <- E J (fp64): rows i = k1 and k1 + 32, pair k2
-        {
-          const double s = sm.s[k2];
-          if (s != 0.0) {
-            const double c = sm.c[k2];
-            int p, q;
-            rr_pair(JS, t, k2, p, q);
+          // E <- E J: rows i = k1 and k1 + 32, pair k2
+          if (s2 != 0.f) {
+            const ET c = sm.c[k2], s = sm.s[k2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int i = k1 + h * H;
-              const double ep = sm.E[i][p], eq = sm.E[i][q];
-              sm.E[i][p] = c * ep - s * eq;
-              sm.E[i][q] = s * ep + c * eq;
+              const ET ep = sm.E[i][p2], eq = sm.E[i][q2];
+              sm.E[i][p2] = c * ep - s * eq;
+              sm.E[i][q2] = s * ep + c * eq;
             }
           }
         }
+        rr_advance(x1, y1, k1);
+        rr_advance(x2, y2, k2);
         __syncthreads();
       }
       if (!sm.rotated) break;
@@ -545,8 +562,11 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
 
   static bool attr_set = false;
   if (!attr_set) {
-    int rc = check_cuda(cudaFuncSetAttribute(svd_evd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(EvdSmem)), "svd_evd attr");
+    int rc = check_cuda(cudaFuncSetAttribute(svd_evd_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(EvdSmem<double>)), "svd_evd attr");
+    if (rc) return rc;
+    rc = check_cuda(cudaFuncSetAttribute(svd_evd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(EvdSmem<float>)), "svd_evd attr");
     if (rc) return rc;
     attr_set = true;
   }
@@ -559,6 +579,8 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
   cudaStream_t st = (cudaStream_t)stream;
   bool use_tc = (prec != GRASP_PREC_SIMT);
   if (const char* e = getenv("GRASP_SVD_TC")) use_tc = atoi(e) != 0;
+  const bool evd64_dbg = getenv("GRASP_SVD_EVD64") != nullptr;      // experiments only
+  const bool no_cleanup_dbg = getenv("GRASP_SVD_NO_CLEANUP") != nullptr;
   if (use_tc) {
     static bool tc_attr = false;
     if (!tc_attr) {
@@ -657,8 +679,12 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
           } else {
             GRASP_LAUNCH(svd_gram_kernel, dim3(g.nsplit, g.npairs, g.nmat), dim3(J_THREADS), 0, st, g, round);
           }
-          GRASP_LAUNCH(svd_evd_kernel, dim3(g.npairs, g.nmat), dim3(EVD_THREADS), sizeof(EvdSmem), st, g, round,
-                       sweep, tol, inner_cap);
+          if (use_tc && !evd64_dbg)
+            GRASP_LAUNCH(svd_evd_kernel<float>, dim3(g.npairs, g.nmat), dim3(EVD_THREADS), sizeof(EvdSmem<float>), st, g,
+                         round, sweep, tol, inner_cap);
+          else
+            GRASP_LAUNCH(svd_evd_kernel<double>, dim3(g.npairs, g.nmat), dim3(EVD_THREADS), sizeof(EvdSmem<double>), st,
+                         g, round, sweep, tol, inner_cap);
           if (use_tc) {
             GRASP_LAUNCH(jacobi_tc_kernel<JT_UPDATE>, dim3(tc_grid_u), dim3(JT_THREADS), JtCfg<JT_UPDATE>::SMEM_BYTES,
                          st, *maps, jp);
@@ -670,7 +696,14 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
         GRASP_LAUNCH(svd_sweep_end_kernel, dim3(1), dim3(32), 0, st, g, sweep, use_tc ? 1e-4f : tol, -1);
       }
       delete maps;
-      if (use_tc) {
+      if (use_tc && no_cleanup_dbg) {
+        for (int j = 0; j < g.nmat; ++j) {
+          const SvdPlan& Q = plans[members[j]];
+          const int64_t n4 = (int64_t)Q.rp * Q.ldz / 4;
+          GRASP_LAUNCH(jt_merge_kernel, dim3((unsigned)ceil_div(n4, 256)), dim3(256), 0, st,
+                       reinterpret_cast<const __nv_bfloat16*>(base[members[j]] + Q.off_Zp), Q.rp, Q.ldz, g.mat[j].Z);
+        }
+      } else if (use_tc) {
         // ---- clean-up.  The tensor-core accumulator truncates, so every update shrinks Z by ~1e-7:
         // after thousands of updates QT is only orthogonal to ~3e-4 and Y has drifted from QT*Y0 by as
         // much.  One Newton-Schulz step re-orthogonalises QT (error -> its square), Y is recomputed as
@@ -706,8 +739,8 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
           const int sweep = max_sweeps + s2;
           for (int round = 0; round < g.p - 1; ++round) {
             GRASP_LAUNCH(svd_gram_kernel, dim3(g.nsplit, g.npairs, g.nmat), dim3(J_THREADS), 0, st, g, round);
-            GRASP_LAUNCH(svd_evd_kernel, dim3(g.npairs, g.nmat), dim3(EVD_THREADS), sizeof(EvdSmem), st, g, round,
-                         sweep, tol, inner_cap);
+            GRASP_LAUNCH(svd_evd_kernel<double>, dim3(g.npairs, g.nmat), dim3(EVD_THREADS), sizeof(EvdSmem<double>), st,
+                         g, round, sweep, tol, inner_cap);
             GRASP_LAUNCH(svd_update_kernel, dim3(g.ldz / UP_TN, g.npairs, g.nmat), dim3(J_THREADS), 0, st, g, round);
           }
           GRASP_LAUNCH(svd_sweep_end_kernel, dim3(1), dim3(32), 0, st, g, sweep, cleanup_conv, s2);

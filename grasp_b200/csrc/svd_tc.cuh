@@ -20,7 +20,7 @@ namespace grasp {
 
 using namespace tc;
 
-constexpr int JT_THREADS = 192;
+constexpr int JT_THREADS = 320;            // TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quadrant)
 constexpr int JT_PLANE_TILE = 128 * 64 * 2;   // 16 KiB: 128 rows (or 64 k-rows x 2 halves) x 64 bf16
 constexpr int JT_NACC = 4;
 
@@ -45,9 +45,13 @@ enum { JT_GRAM = 0, JT_UPDATE = 1 };
 
 template <int MODE>
 struct JtCfg {
-  static constexpr int STAGE_BYTES = (MODE == JT_GRAM ? 3 : 6) * JT_PLANE_TILE;
-  static constexpr int STAGES = (MODE == JT_GRAM) ? 4 : 2;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  // the Gram only steers the rotations of a phase that stops at 1e-4: two planes / three products
+  // (bf16x3, 4e-6) are plenty there; the update keeps all three planes (six products)
+  static constexpr int GRAM_PLANES = 2;
+  static constexpr int STAGE_BYTES = (MODE == JT_GRAM ? GRAM_PLANES : 6) * JT_PLANE_TILE;
+  static constexpr int STAGES = (MODE == JT_GRAM) ? 6 : 2;
+  static constexpr int STORE_BYTES = (MODE == JT_UPDATE) ? 8 * 4096 : 0;   // one 32 x 64 bf16 staging tile per epilogue warp
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_BYTES + 1024 + 256;
 };
 
 // chunk c (0..3) of tile t -> first row of the 32-row block; pairs beyond npairs alias pair 0 of the tile
@@ -78,7 +82,7 @@ jacobi_tc_kernel(const __grid_constant__ JtMaps maps, const JtParams p) {
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < JT_NACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
+    for (int a = 0; a < JT_NACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 256); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(&tmem_base_smem);
@@ -123,7 +127,7 @@ jacobi_tc_kernel(const __grid_constant__ JtMaps maps, const JtParams p) {
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           if (MODE == JT_GRAM) {
 #pragma unroll
-            for (int pl = 0; pl < 3; ++pl)
+            for (int pl = 0; pl < Cfg::GRAM_PLANES; ++pl)
 #pragma unroll
               for (int c = 0; c < 4; ++c)
                 tma_load_4d(st + pl * JT_PLANE_TILE + c * 4096, zmap, &full_bar[stage], (kb & 1) * 64, rows[c], kb >> 1, pl);
@@ -149,8 +153,10 @@ jacobi_tc_kernel(const __grid_constant__ JtMaps maps, const JtParams p) {
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0, MODE == JT_UPDATE ? 1 : 0);
-      constexpr int PA[6] = {2, 0, 1, 1, 0, 0};
-      constexpr int PB[6] = {0, 2, 1, 0, 1, 0};
+      // plane products, small terms first; the Gram uses planes {0,1} only: (1,0) (0,1) (0,0)
+      constexpr int NPROD = (MODE == JT_GRAM) ? 3 : 6;
+      constexpr int PA[6] = {MODE == JT_GRAM ? 1 : 2, 0, MODE == JT_GRAM ? 0 : 1, 1, 0, 0};
+      constexpr int PB[6] = {0, MODE == JT_GRAM ? 1 : 2, MODE == JT_GRAM ? 0 : 1, 0, 1, 0};
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int w = blockIdx.x; w < total; w += gridDim.x) {
@@ -164,7 +170,7 @@ jacobi_tc_kernel(const __grid_constant__ JtMaps maps, const JtParams p) {
           const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t sB = (MODE == JT_GRAM) ? sA : sA + 3 * JT_PLANE_TILE;
 #pragma unroll
-          for (int q = 0; q < 6; ++q) {
+          for (int q = 0; q < NPROD; ++q) {
             const uint64_t da = umma_desc_kmajor_sw128(sA + PA[q] * JT_PLANE_TILE);
             const uint64_t db = (MODE == JT_GRAM) ? umma_desc_kmajor_sw128(sB + PB[q] * JT_PLANE_TILE)
                                                   : umma_desc_mnmajor_sw128(sB + PB[q] * JT_PLANE_TILE, 8192, 1024);
@@ -182,21 +188,22 @@ jacobi_tc_kernel(const __grid_constant__ JtMaps maps, const JtParams p) {
       }
     }
   } else {
-    const int quad = warp & 3;
+    const int quad = warp & 3;                     // TMEM lane quadrant
+    const int half = (warp - 2) >> 2;              // columns [64*half, 64*half + 64) of the tile
     const int mrow = quad * 32 + lane;             // row of the 128-row tile owned by this thread
     int acc = 0; uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       int m, tile, sub, kb0, kb1;
       if (!decode(w, m, tile, sub, kb0, kb1)) continue;
-      float racc[128];
+      float racc[64];
 #pragma unroll
-      for (int j = 0; j < 128; ++j) racc[j] = 0.f;
+      for (int j = 0; j < 64; ++j) racc[j] = 0.f;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&acc_full[acc], acc_phase);
         tc_fence_after_sync();
-        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 128);
+        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 128 + half * 64);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           float t[32];
           tmem_ld_32x32(t_row + (uint32_t)(c * 32), t);
           tmem_ld_wait();
@@ -211,44 +218,56 @@ jacobi_tc_kernel(const __grid_constant__ JtMaps maps, const JtParams p) {
       const int pair = tile * 2 + (mrow >> 6);
       if (pair >= p.npairs) continue;               // second half of an odd last tile
       if (MODE == JT_GRAM) {
-        // keep the 64 x 64 diagonal block of this row's pair
-        float* out = M.Gpart + ((int64_t)pair * p.nsplit + sub) * (JS * JS) + (mrow & 63) * JS;
-        const int c0 = (mrow >> 6) * 64;
+        // the 64 x 64 diagonal block of this row's pair lives in the column half equal to the row half
+        if (half == (mrow >> 6)) {
+          float* out = M.Gpart + ((int64_t)pair * p.nsplit + sub) * (JS * JS) + (mrow & 63) * JS;
 #pragma unroll
-        for (int j = 0; j < 64; j += 4) {
-          float4 v;
-          if (c0 == 0) v = make_float4(racc[j], racc[j + 1], racc[j + 2], racc[j + 3]);
-          else v = make_float4(racc[64 + j], racc[65 + j], racc[66 + j], racc[67 + j]);
-          *reinterpret_cast<float4*>(out + j) = v;
+          for (int j = 0; j < 64; j += 4)
+            *reinterpret_cast<float4*>(out + j) = make_float4(racc[j], racc[j + 1], racc[j + 2], racc[j + 3]);
         }
       } else {
-        const int row = jt_chunk_row(p, tile, mrow >> 5) + (mrow & 31);
-        const int64_t off = ((int64_t)sub * p.rp + row) * 128;          // [column tile][row][128]
-        const int64_t plane = (int64_t)p.rp * p.ldz;
+        // x = p0 + p1 + p2 with p0, p1 the TRUNCATED bf16 of the running remainder (remainders are exact
+        // in fp32) and p2 the truncated rest: |x - sum| <= 2^-24 |x|; a plane word is just the two high
+        // halves of consecutive fp32 bit patterns (one PRMT).  Each warp stages its 32 rows x 64 columns
+        // of one plane in shared memory (128-byte swizzle of the tensor map) and one lane writes the tile
+        // with a TMA store: full 128-byte lines instead of 32 scattered 16-byte pieces per instruction.
+        unsigned char* stg = smem + STAGES * Cfg::STAGE_BYTES + (warp - 2) * 4096;
+        const int row0 = jt_chunk_row(p, tile, quad);       // this warp's 32 rows are chunk `quad` of the tile
 #pragma unroll
-        for (int j = 0; j < 128; j += 8) {
-          uint32_t w0[4], w1[4], w2[4];
+        for (int pl = 0; pl < 3; ++pl) {
+          if (lane == 0) tma_store_wait_read();              // the previous store has finished reading `stg`
+          __syncwarp();
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float x0 = racc[j + 2 * e], x1 = racc[j + 2 * e + 1];
-            const __nv_bfloat16 a0 = __float2bfloat16_rn(x0), b0 = __float2bfloat16_rn(x1);
-            x0 -= __bfloat162float(a0); x1 -= __bfloat162float(b0);
-            const __nv_bfloat16 a1 = __float2bfloat16_rn(x0), b1 = __float2bfloat16_rn(x1);
-            x0 -= __bfloat162float(a1); x1 -= __bfloat162float(b1);
-            const __nv_bfloat16 a2 = __float2bfloat16_rn(x0), b2 = __float2bfloat16_rn(x1);
-            w0[e] = (uint32_t)__bfloat16_as_ushort(a0) | ((uint32_t)__bfloat16_as_ushort(b0) << 16);
-            w1[e] = (uint32_t)__bfloat16_as_ushort(a1) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
-            w2[e] = (uint32_t)__bfloat16_as_ushort(a2) | ((uint32_t)__bfloat16_as_ushort(b2) << 16);
+          for (int j = 0; j < 64; j += 8) {
+            uint32_t wv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float x0 = racc[j + 2 * e], x1 = racc[j + 2 * e + 1];
+              if (pl >= 1) {
+                x0 -= __uint_as_float(__float_as_uint(x0) & 0xffff0000u);
+                x1 -= __uint_as_float(__float_as_uint(x1) & 0xffff0000u);
+              }
+              if (pl == 2) {
+                x0 -= __uint_as_float(__float_as_uint(x0) & 0xffff0000u);
+                x1 -= __uint_as_float(__float_as_uint(x1) & 0xffff0000u);
+              }
+              wv[e] = __byte_perm(__float_as_uint(x0), __float_as_uint(x1), 0x7632);
+            }
+            // 16-byte chunk j/8 of row `lane`, XOR-swizzled with the row index (Swizzle<3,4,3>)
+            *reinterpret_cast<uint4*>(stg + lane * 128 + (((j >> 3) ^ (lane & 7)) << 4)) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
           }
-          __nv_bfloat16* zp = M.Zp + off + j;
-          *reinterpret_cast<uint4*>(zp) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
-          *reinterpret_cast<uint4*>(zp + plane) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
-          *reinterpret_cast<uint4*>(zp + 2 * plane) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&maps.z[m], stg, half * 64, row0, sub, pl);
+            tma_store_commit();
+          }
         }
       }
     }
   }
 
+  if (MODE == JT_UPDATE && warp >= 2 && lane == 0) tma_store_wait_all();
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) {
