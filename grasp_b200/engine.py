@@ -316,10 +316,11 @@ class LlamaRunner:
     def loss_sum(self, hidden, labels, weights):
         """sum_samples w_s * mean_t CE(logits[s, t], labels[s, t+1]): HF's causal-LM loss on the loader's
         already shifted labels (the reference's double shift), one term per sample."""
-        logits = self.head(self.norm(hidden))
-        B, S, V = logits.shape
-        per_tok = F.cross_entropy(logits[:, :-1].reshape(-1, V).float(), labels[:, 1:].reshape(-1), reduction="none")
-        return (per_tok.view(B, S - 1).mean(dim=1) * weights).sum()
+        # only positions [0, S-1) enter the loss: drop the last one before the head instead of slicing the logits
+        logits = self.head(self.norm(hidden[:, :-1]))
+        B, S1, V = logits.shape
+        per_tok = F.cross_entropy(logits.reshape(-1, V).float(), labels[:, 1:].reshape(-1), reduction="none")
+        return (per_tok.view(B, S1).mean(dim=1) * weights).sum()
 
     # ---- prefix cache -------------------------------------------------------------
     def invalidate_above(self, layer_id: int):
