@@ -48,7 +48,7 @@ def parse():
     p.add_argument("--samples", type=int, default=512)
     p.add_argument("--seq-len", type=int, default=512)
     p.add_argument("--ratio", type=float, default=0.9)
-    p.add_argument("--micro-batch", type=int, default=8)
+    p.add_argument("--micro-batch", type=int, default=0, help="0 = chosen from the tile/wave model")
     p.add_argument("--warmup-samples", type=int, default=32)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-svd-dim", type=int, default=0, help="override the CPU sample's matrix size (debug)")
@@ -321,7 +321,7 @@ def run_ours(a):
                 "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32 (fp32 data; GEMMs as 3 fp16-plane tcgen05 products with fp32 accumulation, rel. err 3e-7; SVD bf16x6 planes + fp32 clean-up)",
                 "data": "synthetic",
-                "config": {"workload": workload_name(a), "micro_batch": a.micro_batch,
+                "config": {"workload": workload_name(a), "micro_batch": gm._runner.micro_batch if gm._runner else a.micro_batch,
                            "l2": "inputs larger than L2 (27 GB of weights, 4.3 GB activation cache per layer)",
                            "warmup_samples": min(a.warmup_samples, a.samples), "layers_chosen": gm.redundant_layers,
                            "kept_index_checksum": int(sum(int(v.sum()) * (i + 1) for i, v in

@@ -261,6 +261,20 @@ class CalibrationSet:
         return self.input_ids.shape[0]
 
 
+def auto_micro_batch(seq_len: int, hidden: int, n_sms: int = 148, lo: int = 4, hi: int = 16) -> int:
+    """Samples per micro-batch such that the most frequent GEMM of a block pass (tokens x hidden x hidden,
+    128 x 256 tiles, persistent over n_sms CTAs) fills its last wave best; ties go to the larger batch."""
+    best, best_eff = lo, 0.0
+    n_tiles_n = -(-hidden // 256)
+    for mb in range(lo, hi + 1):
+        tiles = -(-(mb * seq_len) // 128) * n_tiles_n
+        waves = -(-tiles // n_sms)
+        eff = (mb * seq_len * hidden) / (waves * n_sms * 128 * 256)
+        if eff >= best_eff - 1e-9:
+            best, best_eff = mb, eff
+    return best
+
+
 class LlamaRunner:
     """Runs a HF LLaMA-family causal LM layer by layer (same modules, same math as model.forward)."""
 

@@ -133,7 +133,7 @@ class GRASPModel(nn.Module):
         self._svd_cache: Dict[str, tuple] = {}
         # B200 engine state (not part of the reference surface)
         self.use_engine = os.environ.get("GRASP_B200_ENGINE", "1") != "0"
-        self.micro_batch = int(os.environ.get("GRASP_B200_MICRO_BATCH", "8"))
+        self.micro_batch = int(os.environ.get("GRASP_B200_MICRO_BATCH", "0"))   # 0 = pick per calibration set
         self._runner = None
         self._calib = None
 
@@ -150,12 +150,16 @@ class GRASPModel(nn.Module):
         if not self.use_engine or not engine.LlamaRunner.supports(self.model):
             return None
         if self._runner is None:
-            self._runner = engine.LlamaRunner(self.model, micro_batch=self.micro_batch)
+            self._runner = engine.LlamaRunner(self.model, micro_batch=self.micro_batch or 8)
         return self._runner
 
     def _calibration_set(self, dataloader, device):
         if self._calib is None or self._calib[0] is not dataloader:
             self._calib = (dataloader, engine.CalibrationSet(dataloader, device))
+            calib = self._calib[1]
+            if self._runner is not None and calib.supported:
+                hidden = getattr(self.model.config, "hidden_size", 4096)
+                self._runner.micro_batch = self.micro_batch or engine.auto_micro_batch(calib.input_ids.shape[1], hidden)
         return self._calib[1]
 
     def _touched(self, module_name: str):
