@@ -288,6 +288,247 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2) of the two-plane arithmetics: a cluster of two CTAs (two SMs of one
+// TPC) computes a 256 x 256 output tile.  Each CTA loads only ITS 128 rows of A and ITS 128 columns of
+// B (half the B bytes per SM of the single-CTA kernel), the leader CTA issues 256 x 256 x 16 MMAs that
+// read both CTAs' shared memory and write both CTAs' TMEM; each CTA drains its own 128 accumulator rows.
+// Barriers: TMA bytes of both CTAs are counted on the leader's `full` barrier; tcgen05.commit multicasts
+// the `empty` / `acc_full` arrivals to both CTAs; the epilogue warps of both CTAs arrive on the leader's
+// `acc_empty`.
+// ---------------------------------------------------------------------------
+struct Tc2Cfg {
+  static constexpr int NS = 2;
+  static constexpr int TILE = 128 * TC_BK * 2;             // 16 KiB: 128 rows x 64 x 16 bit
+  static constexpr int STAGE_BYTES = NS * 2 * TILE;        // A half + B half per CTA: 64 KiB
+  static constexpr int STAGES = 3;
+  static constexpr int NACC = 2;                           // 2 x 256 TMEM columns
+  static constexpr int THREADS = 64 + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 4 * 256 * 4 + 256;
+};
+
+template <int EPI, int BMN, int F16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Tc2Cfg::THREADS, 1)
+tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcParams p) {
+  using Cfg = Tc2Cfg;
+  constexpr int STAGES = Cfg::STAGES, NACC = Cfg::NACC, NS = Cfg::NS, BN = 256;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  float* red = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);   // [4][256]
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], acc_full[NACC], acc_empty[NACC];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();                   // 0 = leader
+  const int kblocks = (p.K + TC_BK - 1) / TC_BK;
+  const int tiles_m2 = (p.M + 255) / 256;
+  const int total_tiles = tiles_m2 * p.tiles_n;               // p.tiles_n counts 256-wide column tiles
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA);
+    prefetch_tmap(&mapB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < NACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 16); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm<512>(&tmem_base_smem);
+  tc_fence_before_sync();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs) {
+        const int m0 = (tile % tiles_m2) * 256 + (int)rank * 128;
+        const int n0 = (tile / tiles_m2) * BN + (int)rank * 128;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          unsigned char* sA = smem + stage * Cfg::STAGE_BYTES;
+          unsigned char* sB = sA + NS * Cfg::TILE;
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+          else mbar_arrive_cluster(mapa_u32(smem_u32(&full_bar[stage]), 0));
+#pragma unroll
+          for (int pl = 0; pl < NS; ++pl) {
+            tma_load_3d_2sm(sA + pl * Cfg::TILE, &mapA, &full_bar[stage], kb * TC_BK, m0, pl);
+            if constexpr (BMN) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+                tma_load_3d_2sm(sB + pl * Cfg::TILE + h * (TC_BK * 128), &mapB, &full_bar[stage], n0 + h * 64,
+                                kb * TC_BK, pl);
+            } else {
+              tma_load_3d_2sm(sB + pl * Cfg::TILE, &mapB, &full_bar[stage], kb * TC_BK, n0, pl);
+            }
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, BMN, F16);
+      constexpr int PA[3] = {1, 0, 0};
+      constexpr int PB[3] = {0, 1, 0};
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs) {
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+          const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sB = sA + NS * Cfg::TILE;
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const uint64_t da = umma_desc_kmajor_sw128(sA + PA[q] * Cfg::TILE);
+            const uint64_t db = BMN ? umma_desc_mnmajor_sw128(sB + PB[q] * Cfg::TILE, TC_BK * 128, 1024)
+                                    : umma_desc_kmajor_sw128(sB + PB[q] * Cfg::TILE);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              const uint64_t kb_step = BMN ? (uint64_t)(128 * k) : (uint64_t)(2 * k);
+              umma_2sm(d_tmem, da + (uint64_t)(2 * k), db + kb_step, idesc, (q | k) != 0);
+            }
+          }
+          umma_commit_2sm(&empty_bar[stage], 3);   // both CTAs may refill this stage
+          umma_commit_2sm(&acc_full[acc], 3);      // both CTAs' epilogues may drain this accumulator
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..9 of both CTAs)
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int ep_tid = (int)threadIdx.x - 64;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = pair; tile < total_tiles; tile += npairs) {
+      const int m_blk2 = tile % tiles_m2, n_blk = tile / tiles_m2;
+      const int row = m_blk2 * 256 + (int)rank * 128 + quad * 32 + lane;
+      const int n0 = n_blk * BN;
+      float racc[128];
+#pragma unroll
+      for (int j = 0; j < 128; ++j) racc[j] = 0.f;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&acc_full[acc], acc_phase);
+        tc_fence_after_sync();
+        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * 128);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float t[32];
+          tmem_ld_32x32(t_row + (uint32_t)(c * 32), t);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) racc[c * 32 + j] += t[j];
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[acc]), 0));   // leader's barrier
+        if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+      }
+      if constexpr (F16) {
+        const float ia = (row < p.M) ? p.inv_sa[row] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 128; ++j) {
+          const int col = n0 + half * 128 + j;
+          racc[j] *= ia * ((col < p.N) ? __ldg(p.inv_sb + col) : 0.f);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float* v = &racc[c * 32];
+        const int col0 = n0 + half * 128 + c * 32;
+        if constexpr (EPI == EPI_STORE) {
+          if (row < p.M && col0 < p.N) {
+            const int ncols = min(32, p.N - col0);
+            if (p.c_bf16) {
+              __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.C) + (int64_t)row * p.ldc + col0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (j < ncols) {
+                  float x = p.alpha * v[j];
+                  if (p.beta != 0.f) x += p.beta * __bfloat162float(dst[j]);
+                  dst[j] = __float2bfloat16_rn(x);
+                }
+              }
+            } else {
+              float* dst = static_cast<float*>(p.C) + (int64_t)row * p.ldc + col0;
+              const bool vec = (ncols == 32) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+              if (vec) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  float4 o = make_float4(p.alpha * v[j], p.alpha * v[j + 1], p.alpha * v[j + 2], p.alpha * v[j + 3]);
+                  if (p.beta != 0.f) {
+                    const float4 old = *reinterpret_cast<const float4*>(dst + j);
+                    o.x += p.beta * old.x; o.y += p.beta * old.y; o.z += p.beta * old.z; o.w += p.beta * old.w;
+                  }
+                  *reinterpret_cast<float4*>(dst + j) = o;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  if (j < ncols) {
+                    float x = p.alpha * v[j];
+                    if (p.beta != 0.f) x += p.beta * dst[j];
+                    dst[j] = x;
+                  }
+                }
+              }
+            }
+          }
+        } else {
+          const float* u = p.Umul + (int64_t)row * p.ldu + col0;
+          const bool row_ok = row < p.M;
+          const bool vec = row_ok && (col0 + 32 <= p.N) && ((reinterpret_cast<uintptr_t>(u) & 15) == 0);
+          if (vec) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 uu = *reinterpret_cast<const float4*>(u + j);
+              v[j] *= uu.x; v[j + 1] *= uu.y; v[j + 2] *= uu.z; v[j + 3] *= uu.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (row_ok && col0 + j < p.N) ? v[j] * u[j] : 0.f;
+          }
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) {
+#pragma unroll
+            for (int j = 0; j < o; ++j) {
+              const bool up = (lane & o) != 0;
+              const float send = up ? v[j] : v[j + o];
+              const float keep = up ? v[j + o] : v[j];
+              v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+          }
+          red[quad * BN + half * 128 + c * 32 + lane] = v[0];
+        }
+      }
+      if constexpr (EPI == EPI_SIGMA) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int j = ep_tid; j < BN; j += 256) {
+          const int col = n0 + j;
+          if (col < p.N)   // one partial row per 128-row half of the pair tile
+            p.partial[(int64_t)(m_blk2 * 2 + (int)rank) * p.N + col] =
+                (red[j] + red[BN + j]) + (red[2 * BN + j] + red[3 * BN + j]);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc_2sm<512>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // split pre-pass: fp32 [rows x cols] (or its transpose) -> NS bf16 planes [NS][R][Kp]
 // ---------------------------------------------------------------------------
 template <int NS>
@@ -610,6 +851,38 @@ static bool use_bmn() {
   return v != 0;
 }
 
+template <int EPI, int BMN, int F16>
+static int launch_core2(const __nv_bfloat16* Ap, const __nv_bfloat16* Bp, TcParams prm, void* stream) {
+  CUtensorMap mapA, mapB;
+  int rc = make_plane_map(&mapA, Ap, 2, prm.M, prm.K, kp_of(prm.K), 128);
+  if (rc) return rc;
+  if (BMN) rc = make_plane_map(&mapB, Bp, 2, prm.K, prm.N, kp_of(prm.N), TC_BK, 64);
+  else rc = make_plane_map(&mapB, Bp, 2, prm.N, prm.K, kp_of(prm.K), 128);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    rc = check_cuda(cudaFuncSetAttribute(tc_gemm2_kernel<EPI, BMN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Tc2Cfg::SMEM_BYTES), "tc_gemm2 attr");
+    if (rc) return rc;
+    attr_set = true;
+  }
+  prm.tiles_m = (int)ceil_div(prm.M, 256);
+  prm.tiles_n = (int)ceil_div(prm.N, 256);
+  const int pairs_total = prm.tiles_m * prm.tiles_n;
+  const int max_pairs = sm_count() / 2;
+  const int pairs = pairs_total < max_pairs ? pairs_total : max_pairs;
+  GRASP_LAUNCH((tc_gemm2_kernel<EPI, BMN, F16>), dim3(2 * pairs), dim3(Tc2Cfg::THREADS), Tc2Cfg::SMEM_BYTES, stream,
+               mapA, mapB, prm);
+  GRASP_CHECK_LAST("tc_gemm2_kernel");
+  return 0;
+}
+
+static bool use_2cta(int64_t M, int64_t N) {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GRASP_GEMM_2CTA"); v = e ? atoi(e) : 0; }
+  return v != 0 && M > 128 && N > 128;
+}
+
 size_t tc_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int prec) {
   const int NS = ns_of(prec);
   const size_t b = planes_bytes(NS, N, K) > planes_bytes(NS, K, N) ? planes_bytes(NS, N, K) : planes_bytes(NS, K, N);
@@ -651,6 +924,10 @@ int tc_gemm_f32(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, co
     prm.M = (int)M; prm.N = (int)N; prm.K = (int)K;
     prm.alpha = alpha; prm.beta = beta; prm.C = C; prm.ldc = ldc; prm.c_bf16 = c_bf16;
     prm.inv_sa = inv_a; prm.inv_sb = inv_b;
+    if (use_2cta(M, N)) {
+      if (bmn) return launch_core2<EPI_STORE, 1, 1>(Ap, Bp, prm, stream);
+      return launch_core2<EPI_STORE, 0, 1>(Ap, Bp, prm, stream);
+    }
     if (wide_tiles(M, N)) {
       if (bmn) return launch_core<2, 256, EPI_STORE, 1, 1>(Ap, Bp, prm, stream);
       return launch_core<2, 256, EPI_STORE, 0, 1>(Ap, Bp, prm, stream);

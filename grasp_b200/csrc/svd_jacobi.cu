@@ -580,6 +580,12 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
   bool use_tc = (prec != GRASP_PREC_SIMT);
   if (const char* e = getenv("GRASP_SVD_TC")) use_tc = atoi(e) != 0;
   const bool evd64_dbg = getenv("GRASP_SVD_EVD64") != nullptr;      // experiments only
+  int tc_inner_cap = 1;   // one inner Jacobi sweep per pair visit in the tensor-core phase (measured fastest overall)
+  if (const char* e = getenv("GRASP_SVD_TC_INNER_CAP")) tc_inner_cap = atoi(e);
+  // clean-up sweeps on the tensor cores: 10% faster but the accumulator's truncation (also on the exact
+  // identity part, p0+p1+p2 can span more than 24 bits) leaves ~2e-5 instead of ~2e-6 -> off by default
+  bool tc_cleanup = false;
+  if (const char* e = getenv("GRASP_SVD_TC_CLEANUP")) tc_cleanup = atoi(e) != 0;
   const bool no_cleanup_dbg = getenv("GRASP_SVD_NO_CLEANUP") != nullptr;
   if (use_tc) {
     static bool tc_attr = false;
@@ -589,6 +595,9 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
       if (rc) return rc;
       rc = check_cuda(cudaFuncSetAttribute(jacobi_tc_kernel<JT_UPDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            JtCfg<JT_UPDATE>::SMEM_BYTES), "jacobi_tc update attr");
+      if (rc) return rc;
+      rc = check_cuda(cudaFuncSetAttribute(jacobi_tc_kernel<JT_GRAM3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           JtCfg<JT_GRAM3>::SMEM_BYTES), "jacobi_tc gram3 attr");
       if (rc) return rc;
       tc_attr = true;
     }
@@ -681,7 +690,7 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
           }
           if (use_tc && !evd64_dbg)
             GRASP_LAUNCH(svd_evd_kernel<float>, dim3(g.npairs, g.nmat), dim3(EVD_THREADS), sizeof(EvdSmem<float>), st, g,
-                         round, sweep, tol, inner_cap);
+                         round, sweep, tol, tc_inner_cap);
           else
             GRASP_LAUNCH(svd_evd_kernel<double>, dim3(g.npairs, g.nmat), dim3(EVD_THREADS), sizeof(EvdSmem<double>), st,
                          g, round, sweep, tol, inner_cap);
@@ -695,7 +704,6 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
         // tensor-core phase: stop once the Gram is diagonal to 1e-4 (its own drift is of that order anyway)
         GRASP_LAUNCH(svd_sweep_end_kernel, dim3(1), dim3(32), 0, st, g, sweep, use_tc ? 1e-4f : tol, -1);
       }
-      delete maps;
       if (use_tc && no_cleanup_dbg) {
         for (int j = 0; j < g.nmat; ++j) {
           const SvdPlan& Q = plans[members[j]];
@@ -726,26 +734,48 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
           if (rc) break;
           rc = tc_gemm_f32(0, Q.trans ? 1 : 0, Q.rp, Q.L, Q.r, 1.f, QT, Q.ldz, A[i], lda[i], 0.f, Zm, Q.ldz, 0,
                            GRASP_PREC_BF16X6, gws, Q.gws_bytes, stream);
-          g.mat[j].ETp = nullptr;
+          if (!tc_cleanup) g.mat[j].ETp = nullptr;
+          else GRASP_LAUNCH(jt_split_kernel, dim3((unsigned)ceil_div(n4, 256)), dim3(256), 0, st, Zm, Q.rp, Q.ldz,
+                            reinterpret_cast<__nv_bfloat16*>(base[i] + Q.off_Zp));
         }
-        if (rc) break;
+        if (rc) { delete maps; break; }
         GRASP_LAUNCH(svd_reopen_kernel, dim3(1), dim3(32), 0, st, g);
         // after the re-orthogonalisation the Gram is diagonal to ~3e-4, so Jacobi's quadratic convergence
-        // needs two sweeps; the fp32 CUDA-core Gram has a noise floor of ~1e-6 at L = 4096, hence the
-        // looser stopping test (rotations still use `tol`)
+        // needs two sweeps, by default on the CUDA cores (unbiased fp32 FMA; fp64 eigen-solve).
+        // GRASP_SVD_TC_CLEANUP=1 runs them on the tensor cores (three-plane Gram) instead.
         const int extra = 3;
         const float cleanup_conv = 3e-6f;
         for (int s2 = 0; s2 < extra; ++s2) {
           const int sweep = max_sweeps + s2;
           for (int round = 0; round < g.p - 1; ++round) {
-            GRASP_LAUNCH(svd_gram_kernel, dim3(g.nsplit, g.npairs, g.nmat), dim3(J_THREADS), 0, st, g, round);
+            if (tc_cleanup) {
+              jp.round = round;
+              GRASP_LAUNCH(jacobi_tc_kernel<JT_GRAM3>, dim3(tc_grid_g), dim3(JT_THREADS), JtCfg<JT_GRAM3>::SMEM_BYTES, st,
+                           *maps, jp);
+            } else {
+              GRASP_LAUNCH(svd_gram_kernel, dim3(g.nsplit, g.npairs, g.nmat), dim3(J_THREADS), 0, st, g, round);
+            }
             GRASP_LAUNCH(svd_evd_kernel<double>, dim3(g.npairs, g.nmat), dim3(EVD_THREADS), sizeof(EvdSmem<double>), st,
                          g, round, sweep, tol, inner_cap);
-            GRASP_LAUNCH(svd_update_kernel, dim3(g.ldz / UP_TN, g.npairs, g.nmat), dim3(J_THREADS), 0, st, g, round);
+            if (tc_cleanup) {
+              GRASP_LAUNCH(jacobi_tc_kernel<JT_UPDATE>, dim3(tc_grid_u), dim3(JT_THREADS), JtCfg<JT_UPDATE>::SMEM_BYTES,
+                           st, *maps, jp);
+            } else {
+              GRASP_LAUNCH(svd_update_kernel, dim3(g.ldz / UP_TN, g.npairs, g.nmat), dim3(J_THREADS), 0, st, g, round);
+            }
           }
           GRASP_LAUNCH(svd_sweep_end_kernel, dim3(1), dim3(32), 0, st, g, sweep, cleanup_conv, s2);
         }
+        if (tc_cleanup) {
+          for (int j = 0; j < g.nmat; ++j) {
+            const SvdPlan& Q = plans[members[j]];
+            const int64_t n4 = (int64_t)Q.rp * Q.ldz / 4;
+            GRASP_LAUNCH(jt_merge_kernel, dim3((unsigned)ceil_div(n4, 256)), dim3(256), 0, st,
+                         reinterpret_cast<const __nv_bfloat16*>(base[members[j]] + Q.off_Zp), Q.rp, Q.ldz, g.mat[j].Z);
+          }
+        }
       }
+      delete maps;
       rc = check_cuda(cudaGetLastError(), "svd sweep kernels");
       if (rc) break;
     }

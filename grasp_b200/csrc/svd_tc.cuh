@@ -41,15 +41,16 @@ struct JtParams {
   int nmat, rp, Lp, ldz, p, npairs, ntiles, nsplit, round;
 };
 
-enum { JT_GRAM = 0, JT_UPDATE = 1 };
+enum { JT_GRAM = 0, JT_UPDATE = 1, JT_GRAM3 = 2 };   // JT_GRAM3: all three planes / six products (clean-up sweeps)
 
 template <int MODE>
 struct JtCfg {
   // the Gram only steers the rotations of a phase that stops at 1e-4: two planes / three products
   // (bf16x3, 4e-6) are plenty there; the update keeps all three planes (six products)
-  static constexpr int GRAM_PLANES = 2;
-  static constexpr int STAGE_BYTES = (MODE == JT_GRAM ? GRAM_PLANES : 6) * JT_PLANE_TILE;
-  static constexpr int STAGES = (MODE == JT_GRAM) ? 6 : 2;
+  static constexpr bool IS_GRAM = (MODE != JT_UPDATE);
+  static constexpr int GRAM_PLANES = (MODE == JT_GRAM) ? 2 : 3;
+  static constexpr int STAGE_BYTES = (IS_GRAM ? GRAM_PLANES : 6) * JT_PLANE_TILE;
+  static constexpr int STAGES = (MODE == JT_GRAM) ? 6 : (MODE == JT_GRAM3 ? 4 : 2);
   static constexpr int STORE_BYTES = (MODE == JT_UPDATE) ? 8 * 4096 : 0;   // one 32 x 64 bf16 staging tile per epilogue warp
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_BYTES + 1024 + 256;
 };
@@ -77,7 +78,8 @@ jacobi_tc_kernel(const __grid_constant__ JtMaps maps, const JtParams p) {
   const int kblocks_total = p.Lp / 64;
   const int per_split = (kblocks_total + p.nsplit - 1) / p.nsplit;
   const int ncol = p.ldz / 128;
-  const int per_mat = (MODE == JT_GRAM) ? p.ntiles * p.nsplit : p.ntiles * ncol;
+  constexpr bool IS_GRAM = Cfg::IS_GRAM;
+  const int per_mat = IS_GRAM ? p.ntiles * p.nsplit : p.ntiles * ncol;
   const int total = p.nmat * per_mat;
 
   if (warp == 0 && lane == 0) {
@@ -95,7 +97,7 @@ jacobi_tc_kernel(const __grid_constant__ JtMaps maps, const JtParams p) {
   auto decode = [&](int w, int& m, int& tile, int& sub, int& kb0, int& kb1) -> bool {
     m = w / per_mat;
     const int r = w - m * per_mat;
-    if (MODE == JT_GRAM) {
+    if (IS_GRAM) {
       tile = r / p.nsplit; sub = r - tile * p.nsplit;
       kb0 = sub * per_split; kb1 = min(kblocks_total, kb0 + per_split);
     } else {
@@ -108,7 +110,7 @@ jacobi_tc_kernel(const __grid_constant__ JtMaps maps, const JtParams p) {
       const int f1 = (tile * 2 + 1 < p.npairs) ? p.mat[m].pair_flag[tile * 2 + 1] : 0;
       if (!f0 && !f1) return false;                           // both rotations are the identity
     }
-    return kb1 > kb0 || MODE == JT_GRAM;
+    return kb1 > kb0 || IS_GRAM;
   };
 
   if (warp == 0) {
@@ -125,7 +127,7 @@ jacobi_tc_kernel(const __grid_constant__ JtMaps maps, const JtParams p) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          if (MODE == JT_GRAM) {
+          if (IS_GRAM) {
 #pragma unroll
             for (int pl = 0; pl < Cfg::GRAM_PLANES; ++pl)
 #pragma unroll
@@ -157,6 +159,7 @@ jacobi_tc_kernel(const __grid_constant__ JtMaps maps, const JtParams p) {
       constexpr int NPROD = (MODE == JT_GRAM) ? 3 : 6;
       constexpr int PA[6] = {MODE == JT_GRAM ? 1 : 2, 0, MODE == JT_GRAM ? 0 : 1, 1, 0, 0};
       constexpr int PB[6] = {0, MODE == JT_GRAM ? 1 : 2, MODE == JT_GRAM ? 0 : 1, 0, 1, 0};
+      constexpr bool IS_GRAM_ = Cfg::IS_GRAM;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int w = blockIdx.x; w < total; w += gridDim.x) {
@@ -168,15 +171,15 @@ jacobi_tc_kernel(const __grid_constant__ JtMaps maps, const JtParams p) {
           tc_fence_after_sync();
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
           const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t sB = (MODE == JT_GRAM) ? sA : sA + 3 * JT_PLANE_TILE;
+          const uint32_t sB = IS_GRAM_ ? sA : sA + 3 * JT_PLANE_TILE;
 #pragma unroll
           for (int q = 0; q < NPROD; ++q) {
             const uint64_t da = umma_desc_kmajor_sw128(sA + PA[q] * JT_PLANE_TILE);
-            const uint64_t db = (MODE == JT_GRAM) ? umma_desc_kmajor_sw128(sB + PB[q] * JT_PLANE_TILE)
+            const uint64_t db = IS_GRAM_ ? umma_desc_kmajor_sw128(sB + PB[q] * JT_PLANE_TILE)
                                                   : umma_desc_mnmajor_sw128(sB + PB[q] * JT_PLANE_TILE, 8192, 1024);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const uint64_t bstep = (MODE == JT_GRAM) ? (uint64_t)(2 * k) : (uint64_t)(128 * k);
+              const uint64_t bstep = IS_GRAM_ ? (uint64_t)(2 * k) : (uint64_t)(128 * k);
               umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + bstep, idesc, (q | k) != 0);
             }
           }
@@ -217,7 +220,7 @@ jacobi_tc_kernel(const __grid_constant__ JtMaps maps, const JtParams p) {
       const JtMat& M = p.mat[m];
       const int pair = tile * 2 + (mrow >> 6);
       if (pair >= p.npairs) continue;               // second half of an odd last tile
-      if (MODE == JT_GRAM) {
+      if (IS_GRAM) {
         // the 64 x 64 diagonal block of this row's pair lives in the column half equal to the row half
         if (half == (mrow >> 6)) {
           float* out = M.Gpart + ((int64_t)pair * p.nsplit + sub) * (JS * JS) + (mrow & 63) * JS;
