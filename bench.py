@@ -303,7 +303,10 @@ def run_ours(a):
             pass
         roof = None
         if kt:
-            tag, rec = max(kt.items(), key=lambda kv: kv[1]["ms"])
+            # the dominant single kernel: the tensor-core GEMM (the SVD entry is a composite of ~10 kernels
+            # per Jacobi round and is reported beside it)
+            gemm_tags = {k: v for k, v in kt.items() if k.startswith("grasp_gemm_f")}
+            tag, rec = max((gemm_tags or kt).items(), key=lambda kv: kv[1]["ms"])
             peak = peaks.get("bf16_tflops_sustained", 1400.0)
             achieved = rec["flops"] / (rec["ms"] * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": tag, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",

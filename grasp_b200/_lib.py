@@ -11,6 +11,7 @@ _LIB_PATH = Path(__file__).resolve().parent / "libgrasp_b200.so"
 PREC_SIMT, PREC_BF16X3, PREC_BF16X6, PREC_F16X3 = 0, 3, 6, 16
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 METRIC_GRADIENT, METRIC_TAYLOR = 0, 1
+SCALE_ROWS, SCALE_TENSOR = 0, 2
 
 _i64p = C.POINTER(C.c_int64)
 _vpp = C.POINTER(C.c_void_p)
@@ -44,6 +45,20 @@ SIGNATURES = {
     "grasp_gemm_f32": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_void_p, C.c_int64,
                                  C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
                                  C.c_size_t, C.c_void_p]),
+    "grasp_gemm_planes_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
+    "grasp_gemm_split_f16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
+    "grasp_gemm_f16x3_planes": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_int64, C.c_void_p]),
+    "grasp_rmsnorm_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_float, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]),
+    "grasp_rmsnorm_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                    C.c_void_p, C.c_void_p]),
+    "grasp_rope_inplace": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                     C.c_int64, C.c_int, C.c_void_p]),
+    "grasp_swiglu_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "grasp_swiglu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "grasp_ce_loss_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
 }
 
 

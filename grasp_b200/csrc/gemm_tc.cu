@@ -957,6 +957,163 @@ int tc_gemm_f32(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, co
   return launch_core<3, 128, EPI_STORE>(Ap, Bp, prm, stream);
 }
 
+// ---------------------------------------------------------------------------
+// Prepared operands (F16X3 arithmetic).  The calibration engine multiplies the same weight by many
+// micro-batches (forward as [N][K], backward as [K][N]) and the same activation by several weights, so the
+// split pre-pass is exposed on its own: planes [2][rows][round8(cols)] fp16 in the STORED orientation plus
+// inverse scales.  Scale per stored row (activations: one read of the row, staged in shared memory) or one
+// scale for the whole tensor (weights: the same planes then serve as K-major and as MN-major operand).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rowsplit_f16_kernel(const float* __restrict__ src, int64_t ld, int R, int K, int Kp, uint16_t* __restrict__ planes,
+                    float* __restrict__ inv) {
+  extern __shared__ __align__(16) float rowbuf[];     // Kp floats
+  __shared__ float red[8];
+  __shared__ float s_scale;
+  const int r = blockIdx.x;
+  const float* row = src + (int64_t)r * ld;
+  float m = 0.f;
+  const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  if (vec) {
+    for (int k = threadIdx.x * 4; k < Kp; k += 256 * 4) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k + 3 < K) v = ldg_stream(reinterpret_cast<const float4*>(row + k));
+      else { if (k < K) v.x = row[k]; if (k + 1 < K) v.y = row[k + 1]; if (k + 2 < K) v.z = row[k + 2]; }
+      *reinterpret_cast<float4*>(rowbuf + k) = v;
+      m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+  } else {
+    for (int k = threadIdx.x; k < Kp; k += 256) {
+      const float v = (k < K) ? row[k] : 0.f;
+      rowbuf[k] = v;
+      m = fmaxf(m, fabsf(v));
+    }
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = (threadIdx.x < 8) ? red[threadIdx.x] : 0.f;
+    v = warp_max(v);
+    if (threadIdx.x == 0) {
+      float s, i;
+      scale_from_max(v, s, i);
+      s_scale = s;
+      inv[r] = i;
+    }
+  }
+  __syncthreads();
+  const float s = s_scale;
+  uint16_t* d0 = planes + (int64_t)r * Kp;
+  uint16_t* d1 = d0 + (int64_t)R * Kp;
+  for (int k = threadIdx.x * 8; k < Kp; k += 256 * 8) {     // Kp % 8 == 0: 16-byte stores
+    uint16_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) split_f16(rowbuf[k + j] * s, hi[j], lo[j]);
+    uint4 w;
+    w.x = hi[0] | ((uint32_t)hi[1] << 16); w.y = hi[2] | ((uint32_t)hi[3] << 16);
+    w.z = hi[4] | ((uint32_t)hi[5] << 16); w.w = hi[6] | ((uint32_t)hi[7] << 16);
+    *reinterpret_cast<uint4*>(d0 + k) = w;
+    w.x = lo[0] | ((uint32_t)lo[1] << 16); w.y = lo[2] | ((uint32_t)lo[3] << 16);
+    w.z = lo[4] | ((uint32_t)lo[5] << 16); w.w = lo[6] | ((uint32_t)lo[7] << 16);
+    *reinterpret_cast<uint4*>(d1 + k) = w;
+  }
+}
+
+// bits of max |src| over the whole tensor (non-negative floats order like their bit patterns)
+__global__ void absmax_bits_kernel(const float* __restrict__ src, int64_t ld, int R, int K, uint32_t* __restrict__ out) {
+  float m = 0.f;
+  for (int r = blockIdx.x; r < R; r += gridDim.x)
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      const float v = fabsf(src[(int64_t)r * ld + k]);
+      if (v == v) m = fmaxf(m, v);
+    }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+
+__global__ void tensorsplit_f16_kernel(const float* __restrict__ src, int64_t ld, int R, int K, int Kp,
+                                       const uint32_t* __restrict__ maxbits, uint16_t* __restrict__ planes,
+                                       float* __restrict__ inv, int n_inv) {
+  float s, i;
+  scale_from_max(__uint_as_float(*maxbits), s, i);
+  const int r = blockIdx.y;
+  const int k0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (r == 0)
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_inv; j += gridDim.x * blockDim.x) inv[j] = i;
+  if (k0 >= Kp) return;
+  const float* srow = src + (int64_t)r * ld + k0;
+  uint16_t hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split_f16((k0 + j < K) ? srow[j] * s : 0.f, hi[j], lo[j]);
+  uint16_t* d = planes + (int64_t)r * Kp + k0;
+  uint2 w;
+  w.x = (uint32_t)hi[0] | ((uint32_t)hi[1] << 16); w.y = (uint32_t)hi[2] | ((uint32_t)hi[3] << 16);
+  *reinterpret_cast<uint2*>(d) = w;
+  w.x = (uint32_t)lo[0] | ((uint32_t)lo[1] << 16); w.y = (uint32_t)lo[2] | ((uint32_t)lo[3] << 16);
+  *reinterpret_cast<uint2*>(d + (int64_t)R * Kp) = w;
+}
+
+size_t tc_planes_bytes(int64_t rows, int64_t cols) { return planes_bytes(2, rows, cols); }
+
+int tc_split_f16(const float* src, int64_t ld, int64_t rows, int64_t cols, int scale_mode, void* planes, float* inv,
+                 void* stream) {
+  if (rows <= 0 || cols <= 0 || rows >= (1 << 30) || cols >= (1 << 30)) return bad_arg("split: rows/cols");
+  if (reinterpret_cast<uintptr_t>(planes) & 1023) return bad_arg("split: planes must be 1024-byte aligned");
+  const int R = (int)rows, K = (int)cols, Kp = kp_of(cols);
+  uint16_t* pl = static_cast<uint16_t*>(planes);
+  if (scale_mode == GRASP_SCALE_ROWS) {
+    const size_t smem = (size_t)Kp * 4;
+    if (smem > 200 * 1024) return bad_arg("split: row longer than 51200 elements");
+    static size_t attr = 48 * 1024;
+    if (smem > attr) {
+      int rc = check_cuda(cudaFuncSetAttribute(rowsplit_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+                          "rowsplit attr");
+      if (rc) return rc;
+      attr = 200 * 1024;
+    }
+    GRASP_LAUNCH(rowsplit_f16_kernel, dim3((unsigned)R), dim3(256), smem, stream, src, ld, R, K, Kp, pl, inv);
+    GRASP_CHECK_LAST("rowsplit_f16_kernel");
+    return 0;
+  }
+  if (scale_mode != GRASP_SCALE_TENSOR) return bad_arg("split: scale_mode");
+  // inv holds max(rows, cols) entries followed by one scratch word for the maximum
+  const int n_inv = (int)(rows > cols ? rows : cols);
+  uint32_t* maxbits = reinterpret_cast<uint32_t*>(inv + n_inv);
+  int rc = check_cuda(cudaMemsetAsync(maxbits, 0, 4, (cudaStream_t)stream), "split memset");
+  if (rc) return rc;
+  GRASP_LAUNCH(absmax_bits_kernel, dim3((unsigned)(R < 1184 ? R : 1184)), dim3(256), 0, stream, src, ld, R, K, maxbits);
+  GRASP_LAUNCH(tensorsplit_f16_kernel, dim3((unsigned)ceil_div(Kp, 4 * 256), (unsigned)R), dim3(256), 0, stream, src, ld,
+               R, K, Kp, (const uint32_t*)maxbits, pl, inv, n_inv);
+  GRASP_CHECK_LAST("tensor split kernels");
+  return 0;
+}
+
+// C = alpha * A op(B) + beta * C on prepared operands.  A planes [2][M][Kp]; B planes [2][N][Kp] (b_kn = 0)
+// or [2][K][Np] (b_kn = 1); inv_a [M], inv_b [N].
+int tc_gemm_planes(int64_t M, int64_t N, int64_t K, float alpha, const void* Ap, const float* inv_a, const void* Bp,
+                   int b_kn, const float* inv_b, float beta, float* C, int64_t ldc, void* stream) {
+  if (!dims_ok(M, N, K)) return bad_arg("gemm_planes: M/N/K");
+  if ((reinterpret_cast<uintptr_t>(Ap) & 1023) || (reinterpret_cast<uintptr_t>(Bp) & 1023))
+    return bad_arg("gemm_planes: planes must be 1024-byte aligned");
+  TcParams prm{};
+  prm.M = (int)M; prm.N = (int)N; prm.K = (int)K;
+  prm.alpha = alpha; prm.beta = beta; prm.C = C; prm.ldc = ldc; prm.c_bf16 = 0;
+  prm.inv_sa = inv_a; prm.inv_sb = inv_b;
+  const __nv_bfloat16* A16 = static_cast<const __nv_bfloat16*>(Ap);
+  const __nv_bfloat16* B16 = static_cast<const __nv_bfloat16*>(Bp);
+  if (use_2cta(M, N)) {
+    if (b_kn) return launch_core2<EPI_STORE, 1, 1>(A16, B16, prm, stream);
+    return launch_core2<EPI_STORE, 0, 1>(A16, B16, prm, stream);
+  }
+  if (wide_tiles(M, N)) {
+    if (b_kn) return launch_core<2, 256, EPI_STORE, 1, 1>(A16, B16, prm, stream);
+    return launch_core<2, 256, EPI_STORE, 0, 1>(A16, B16, prm, stream);
+  }
+  if (b_kn) return launch_core<2, 128, EPI_STORE, 1, 1>(A16, B16, prm, stream);
+  return launch_core<2, 128, EPI_STORE, 0, 1>(A16, B16, prm, stream);
+}
+
 int tc_sigma_partials(const float* U, const float* G, const float* Vh, int64_t out, int64_t in, int64_t r, int prec,
                       float* partial, int64_t* n_partials, void* ws, size_t ws_bytes, void* stream) {
   if (!dims_ok(out, r, in)) return bad_arg("tc_sigma: out/in/r");

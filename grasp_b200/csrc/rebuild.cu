@@ -11,6 +11,11 @@ int tc_gemm_f32(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, co
                 const float* B, int64_t ldb, float beta, void* C, int64_t ldc, int c_bf16, int prec, void* ws,
                 size_t ws_bytes, void* stream);
 size_t tc_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int prec);
+size_t tc_planes_bytes(int64_t rows, int64_t cols);
+int tc_split_f16(const float* src, int64_t ld, int64_t rows, int64_t cols, int scale_mode, void* planes, float* inv,
+                 void* stream);
+int tc_gemm_planes(int64_t M, int64_t N, int64_t K, float alpha, const void* Ap, const float* inv_a, const void* Bp,
+                   int b_kn, const float* inv_b, float beta, float* C, int64_t ldc, void* stream);
 
 // Uk[a][j] = U[a][idx[j]] * su(j),  j < kp (zero beyond k);  su = 1 (mode 0) or sqrt(S) (mode 1)
 __global__ void gather_cols_kernel(const float* __restrict__ U, const float* __restrict__ S,
@@ -126,4 +131,24 @@ extern "C" int grasp_gemm_f32(int ta, int tb, int64_t M, int64_t N, int64_t K, f
   }
   if (prec != GRASP_PREC_BF16X3 && prec != GRASP_PREC_BF16X6 && prec != GRASP_PREC_F16X3) return bad_arg("gemm: prec");
   return tc_gemm_f32(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 0, prec, ws, ws_bytes, stream);
+}
+
+extern "C" size_t grasp_gemm_planes_bytes(int64_t rows, int64_t cols) {
+  if (rows <= 0 || cols <= 0) return 0;
+  return tc_planes_bytes(rows, cols);
+}
+
+extern "C" int grasp_gemm_split_f16(const float* src, int64_t ld, int64_t rows, int64_t cols, int scale_mode,
+                                    void* planes, float* inv, void* stream) {
+  if (!src || !planes || !inv) return bad_arg("split: null");
+  if (ld < cols) return bad_arg("split: leading dimension");
+  return tc_split_f16(src, ld, rows, cols, scale_mode, planes, inv, stream);
+}
+
+extern "C" int grasp_gemm_f16x3_planes(int64_t M, int64_t N, int64_t K, float alpha, const void* A_planes,
+                                       const float* inv_a, const void* B_planes, int b_kn, const float* inv_b,
+                                       float beta, float* C, int64_t ldc, void* stream) {
+  if (!A_planes || !B_planes || !inv_a || !inv_b || !C) return bad_arg("gemm_planes: null");
+  if (ldc < N) return bad_arg("gemm_planes: leading dimension");
+  return tc_gemm_planes(M, N, K, alpha, A_planes, inv_a, B_planes, b_kn, inv_b, beta, C, ldc, stream);
 }

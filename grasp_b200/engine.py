@@ -13,6 +13,7 @@ them to autograd / per-call library dispatch:
 from __future__ import annotations
 
 import contextlib
+import os
 from collections import OrderedDict
 from typing import Iterable, List, Sequence
 
@@ -278,8 +279,12 @@ def auto_micro_batch(seq_len: int, hidden: int, n_sms: int = 148, lo: int = 4, h
 class LlamaRunner:
     """Runs a HF LLaMA-family causal LM layer by layer (same modules, same math as model.forward)."""
 
-    def __init__(self, hf_model, micro_batch: int = 8, use_grasp_gemm: bool = True):
+    def __init__(self, hf_model, micro_batch: int = 8, use_grasp_gemm: bool = True, use_fused=None):
         self.hf = hf_model
+        # explicit forward/backward on the row kernels + prepared-operand GEMMs (fused.py); the transformers
+        # modules + autograd route below stays as the generic fallback and as the cross-check in the tests
+        self.use_fused = (os.environ.get("GRASP_B200_FUSED", "1") != "0") if use_fused is None else bool(use_fused)
+        self._fused = None
         m = hf_model.model
         self.embed, self.layers, self.norm, self.rotary, self.head = (m.embed_tokens, m.layers, m.norm, m.rotary_emb,
                                                                       hf_model.lm_head)
@@ -301,6 +306,16 @@ class LlamaRunner:
     def n_layers(self):
         return len(self.layers)
 
+    def fused(self, like: torch.Tensor):
+        """The fused executor when it applies to activations like `like` (fp32 on a CUDA device, every
+        module of a known kind), else None."""
+        if not (self.use_fused and self.use_grasp_gemm and like.is_cuda and like.dtype == torch.float32):
+            return None
+        if self._fused is None:
+            from .fused import FusedLlama
+            self._fused = FusedLlama(self)
+        return self._fused if self._fused.supported() else None
+
     def _pos(self, hidden):
         position_ids = torch.arange(hidden.shape[1], device=hidden.device).unsqueeze(0)
         return position_ids, self.rotary(hidden, position_ids=position_ids)
@@ -316,11 +331,19 @@ class LlamaRunner:
             hidden = self._layer(i, hidden, position_ids, pos_emb)
         return hidden
 
-    def hidden_states(self, input_ids):
+    def hidden_states(self, input_ids, fused=None):
         """The L+1 states HF returns with output_hidden_states=True (last one after the final norm)."""
         hidden = self.embed(input_ids)
         position_ids, pos_emb = self._pos(hidden)
         states = [hidden]
+        if fused is not None:
+            B, S, d = hidden.shape
+            x = hidden.reshape(B * S, d)
+            for i in range(self.n_layers):
+                x, _ = fused.layer_fwd(i, x, B, S, pos_emb[0], pos_emb[1], keep=False)
+                states.append(x.view(B, S, d))
+            states[-1] = fused.final_norm(x).view(B, S, d)
+            return states
         for i in range(self.n_layers):
             hidden = self._layer(i, hidden, position_ids, pos_emb)
             states.append(hidden)
@@ -342,6 +365,8 @@ class LlamaRunner:
         for store in (self.cache, self.ckpt):
             for k in [k for k in store if k > layer_id]:
                 del store[k]
+        if self._fused is not None and hasattr(self._fused.be, "drop_weights"):
+            self._fused.be.drop_weights(layer_id)          # its modules were replaced: cached planes are stale
 
     def build_cache(self, calib: CalibrationSet, layer_ids):
         if self.cache_key != id(calib):
@@ -355,6 +380,7 @@ class LlamaRunner:
         starts = [c for c in ckpt if c <= need[0]]
         start = max(starts) if starts else None
         with torch.no_grad(), grasp_linear(self.use_grasp_gemm):
+            fused = None
             for s in range(0, n, self.micro_batch):
                 ids = calib.input_ids[s:s + self.micro_batch]
                 if start is None:
@@ -362,6 +388,8 @@ class LlamaRunner:
                 else:
                     hidden, first = ckpt[start][s:s + ids.shape[0]], start
                 position_ids, pos_emb = self._pos(hidden)
+                if s == 0:
+                    fused = self.fused(hidden)
                 for i in range(first, need[-1] + 1):
                     if i in need:
                         if i not in self.cache:
@@ -369,7 +397,12 @@ class LlamaRunner:
                                                         device=hidden.device)
                         self.cache[i][s:s + ids.shape[0]] = hidden
                     if i < need[-1]:
-                        hidden = self._layer(i, hidden, position_ids, pos_emb)
+                        if fused is not None:
+                            B, S, d = hidden.shape
+                            hidden = fused.layer_fwd(i, hidden.reshape(B * S, d), B, S, pos_emb[0], pos_emb[1],
+                                                     keep=False)[0].view(B, S, d)
+                        else:
+                            hidden = self._layer(i, hidden, position_ids, pos_emb)
         self.ckpt, self.ckpt_key = {}, None      # checkpoints served their purpose: release the memory
 
     def _plan_checkpoints(self, calib: CalibrationSet, hidden_shape, element_size):
@@ -390,9 +423,10 @@ class LlamaRunner:
         self.ckpt, self.ckpt_key = {}, id(calib)
         plan = None
         with torch.no_grad(), grasp_linear(self.use_grasp_gemm):
+            fused = self.fused(self.embed(calib.input_ids[:1])) if len(calib) else None
             for s in range(0, len(calib), self.micro_batch):
                 ids = calib.input_ids[s:s + self.micro_batch]
-                states = self.hidden_states(ids)
+                states = self.hidden_states(ids, fused)
                 if plan is None:
                     plan = self._plan_checkpoints(calib, states[0].shape, states[0].element_size())
                     for l in plan:
@@ -413,6 +447,15 @@ class LlamaRunner:
         """dL/dS of the GRASPLayers in `layers` (name -> module), all of them at or above start_layer."""
         self.build_cache(calib, [start_layer])
         src = self.cache[start_layer]
+        fused = self.fused(src)
+        if fused is not None:
+            with deferred_sigma_grads(layers.values()), torch.no_grad():
+                for s in range(0, len(calib), self.micro_batch):
+                    fused.forward_backward(src[s:s + self.micro_batch], calib.labels[s:s + self.micro_batch],
+                                           calib.weights[s:s + self.micro_batch], start_layer, start_layer)
+                grads = {name: contract_sigma_grad(layer) for name, layer in layers.items()}
+            dist.all_reduce_sum_many_(list(grads.values()))
+            return grads
         with deferred_sigma_grads(layers.values()), grasp_linear(self.use_grasp_gemm):
             for s in range(0, len(calib), self.micro_batch):
                 hidden = self.run_layers(src[s:s + self.micro_batch], start_layer, self.n_layers)

@@ -385,3 +385,189 @@ def gemm(A: torch.Tensor, B: torch.Tensor, ta: bool = False, tb: bool = False, a
         timers.stop("grasp_gemm_f32", t0, flops=2.0 * M * N * K, mma_per_flop=_mma_per_flop(p))
     ws.record_stream(torch.cuda.current_stream())
     return C_out
+
+
+# ------------------------------------------------------- prepared GEMM operands
+class Operand:
+    """fp16 (hi, lo) planes + inverse scales of one fp32 matrix in its stored orientation
+    (include/grasp_b200.h, grasp_gemm_split_f16).  `src` keeps the source storage alive."""
+    __slots__ = ("planes", "inv", "rows", "cols", "mode", "src", "version", "_base")
+
+    def nbytes(self) -> int:
+        return self._base.numel() + self.inv.numel() * 4
+
+
+def split_f16(x: torch.Tensor, mode: int = _lib.SCALE_ROWS, keep_src: bool = False) -> Operand:
+    """Planes of a contiguous fp32 [rows, cols] matrix; SCALE_ROWS for activations, SCALE_TENSOR for weights."""
+    lib = _lib.load()
+    dev = _need_cuda(x)
+    if x.dim() != 2:
+        raise ValueError("split_f16 expects a 2-D matrix")
+    x = _f32c(x, "x")
+    rows, cols = x.shape
+    if rows == 0 or cols == 0:
+        raise ValueError("split_f16: empty matrix")
+    nbytes = lib.grasp_gemm_planes_bytes(rows, cols)
+    base = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+    off = (-base.data_ptr()) % 1024
+    op = Operand()
+    op._base = base
+    op.planes = base.data_ptr() + off
+    n_inv = rows if mode == _lib.SCALE_ROWS else max(rows, cols) + 1
+    op.inv = torch.empty(n_inv, dtype=torch.float32, device=dev)
+    op.rows, op.cols, op.mode = rows, cols, mode
+    op.src = x if keep_src else None
+    op.version = x._version
+    with torch.cuda.device(dev):
+        t0 = timers.start()
+        check(lib.grasp_gemm_split_f16(x.data_ptr(), cols, rows, cols, int(mode), op.planes, op.inv.data_ptr(),
+                                       _stream()), "grasp_gemm_split_f16")
+        timers.stop("grasp_gemm_split_f16", t0, bytes_=8.0 * rows * cols)
+    return op
+
+
+def gemm_planes(a: Operand, b: Operand, b_kn: bool = False, alpha: float = 1.0, beta: float = 0.0,
+                C_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """C = alpha * A op(B) + beta * C on prepared operands: b_kn=False -> B stored [N, K] (x W^T);
+    b_kn=True -> B stored [K, N] (dy W), which needs a tensor-scaled B."""
+    lib = _lib.load()
+    M, K = a.rows, a.cols
+    if b_kn:
+        K2, N = b.rows, b.cols
+        if b.mode != _lib.SCALE_TENSOR:
+            raise ValueError("a [K, N] operand must be tensor-scaled")
+    else:
+        N, K2 = b.rows, b.cols
+    if K != K2:
+        raise ValueError(f"inner dimensions differ: {K} vs {K2}")
+    dev = a.inv.device
+    if C_out is None:
+        if beta != 0.0:
+            raise ValueError("beta != 0 needs C_out")
+        C_out = torch.empty(M, N, dtype=torch.float32, device=dev)
+    elif C_out.dtype != torch.float32 or not C_out.is_contiguous() or C_out.shape != (M, N) or not C_out.is_cuda:
+        raise TypeError("C_out must be a contiguous float32 CUDA [M,N] tensor")
+    with torch.cuda.device(dev):
+        t0 = timers.start()
+        check(lib.grasp_gemm_f16x3_planes(M, N, K, float(alpha), a.planes, a.inv.data_ptr(), b.planes, int(bool(b_kn)),
+                                          b.inv.data_ptr(), float(beta), C_out.data_ptr(), N, _stream()),
+              "grasp_gemm_f16x3_planes")
+        timers.stop("grasp_gemm_f16x3_planes", t0, flops=2.0 * M * N * K, mma_per_flop=3.0)
+    return C_out
+
+
+# ------------------------------------------------------- decoder-layer row kernels
+def _rows2d(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dim() != 2:
+        raise ValueError(f"{name} must be 2-D")
+    return _f32c(t, name)
+
+
+def rmsnorm_fwd(x: torch.Tensor, w: torch.Tensor, eps: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    lib = _lib.load()
+    dev = _need_cuda(x, w)
+    x, w = _rows2d(x, "x"), _f32c(w, "w")
+    rows, d = x.shape
+    y = torch.empty_like(x)
+    rstd = torch.empty(rows, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        t0 = timers.start()
+        check(lib.grasp_rmsnorm_fwd(x.data_ptr(), w.data_ptr(), rows, d, float(eps), y.data_ptr(), rstd.data_ptr(),
+                                    _stream()), "grasp_rmsnorm_fwd")
+        timers.stop("grasp_rowops", t0, bytes_=8.0 * rows * d)
+    return y, rstd
+
+
+def rmsnorm_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, rstd: torch.Tensor,
+                add: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    dev = _need_cuda(dy, x, w, rstd, add)
+    dy, x, w, rstd = _rows2d(dy, "dy"), _rows2d(x, "x"), _f32c(w, "w"), _f32c(rstd, "rstd")
+    if add is not None:
+        add = _rows2d(add, "add")
+    rows, d = x.shape
+    dx = torch.empty_like(x)
+    with torch.cuda.device(dev):
+        t0 = timers.start()
+        check(lib.grasp_rmsnorm_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), rstd.data_ptr(),
+                                    add.data_ptr() if add is not None else None, rows, d, dx.data_ptr(), _stream()),
+              "grasp_rmsnorm_bwd")
+        timers.stop("grasp_rowops", t0, bytes_=(12.0 + (4.0 if add is not None else 0.0)) * rows * d)
+    return dx
+
+
+def rope_(x: torch.Tensor, seq: int, heads: int, hd: int, cos: torch.Tensor, sin: torch.Tensor,
+          inverse: bool = False) -> torch.Tensor:
+    """In place on x [tokens, heads*hd]; cos/sin [1 or B, seq, hd]."""
+    lib = _lib.load()
+    dev = _need_cuda(x, cos, sin)
+    if x.dtype != torch.float32 or not x.is_contiguous() or x.dim() != 2 or x.shape[1] != heads * hd:
+        raise TypeError("rope_: x must be a contiguous float32 [tokens, heads*hd] tensor")
+    cos, sin = _f32c(cos, "cos"), _f32c(sin, "sin")
+    if cos.shape[-2:] != (seq, hd) or sin.shape != cos.shape:
+        raise ValueError("rope_: cos/sin must be [*, seq, head_dim]")
+    batch = cos.shape[0] if cos.dim() == 3 else 1
+    cs_batch = 0 if batch == 1 else seq * hd
+    tokens = x.shape[0]
+    if batch != 1 and batch * seq != tokens:
+        raise ValueError("rope_: cos/sin batch does not match the token count")
+    with torch.cuda.device(dev):
+        t0 = timers.start()
+        check(lib.grasp_rope_inplace(x.data_ptr(), tokens, seq, heads, hd, cos.data_ptr(), sin.data_ptr(), cs_batch,
+                                     int(bool(inverse)), _stream()), "grasp_rope_inplace")
+        timers.stop("grasp_rowops", t0, bytes_=8.0 * x.numel())
+    return x
+
+
+def swiglu_fwd(g: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    dev = _need_cuda(g, u)
+    g, u = _f32c(g, "g"), _f32c(u, "u")
+    if g.shape != u.shape:
+        raise ValueError("swiglu: shapes differ")
+    h = torch.empty_like(g)
+    with torch.cuda.device(dev):
+        t0 = timers.start()
+        check(lib.grasp_swiglu_fwd(g.data_ptr(), u.data_ptr(), g.numel(), h.data_ptr(), _stream()), "grasp_swiglu_fwd")
+        timers.stop("grasp_rowops", t0, bytes_=12.0 * g.numel())
+    return h
+
+
+def swiglu_bwd(dh: torch.Tensor, g: torch.Tensor, u: torch.Tensor, inplace: bool = False):
+    """(dg, du); inplace=True overwrites g and u with their gradients."""
+    lib = _lib.load()
+    dev = _need_cuda(dh, g, u)
+    dh = _f32c(dh, "dh")
+    if g.dtype != torch.float32 or u.dtype != torch.float32 or not g.is_contiguous() or not u.is_contiguous():
+        raise TypeError("swiglu_bwd: g and u must be contiguous float32")
+    if g.shape != u.shape or dh.shape != g.shape:
+        raise ValueError("swiglu: shapes differ")
+    dg = g if inplace else torch.empty_like(g)
+    du = u if inplace else torch.empty_like(u)
+    with torch.cuda.device(dev):
+        t0 = timers.start()
+        check(lib.grasp_swiglu_bwd(dh.data_ptr(), g.data_ptr(), u.data_ptr(), g.numel(), dg.data_ptr(), du.data_ptr(),
+                                   _stream()), "grasp_swiglu_bwd")
+        timers.stop("grasp_rowops", t0, bytes_=20.0 * g.numel())
+    return dg, du
+
+
+def ce_loss_bwd_(logits: torch.Tensor, labels: torch.Tensor, coef: torch.Tensor) -> torch.Tensor:
+    """loss[t] = coef[t] * CE(logits[t], labels[t]); logits is overwritten by dloss/dlogits.  labels < 0 are ignored."""
+    lib = _lib.load()
+    dev = _need_cuda(logits, labels, coef)
+    if logits.dtype != torch.float32 or not logits.is_contiguous() or logits.dim() != 2:
+        raise TypeError("ce_loss_bwd_: logits must be a contiguous float32 [rows, V] tensor")
+    if labels.dtype != torch.int64:
+        raise TypeError("ce_loss_bwd_: labels must be int64")
+    labels, coef = labels.contiguous(), _f32c(coef, "coef")
+    rows, V = logits.shape
+    if labels.numel() != rows or coef.numel() != rows:
+        raise ValueError("ce_loss_bwd_: one label and one coefficient per row")
+    loss = torch.empty(rows, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        t0 = timers.start()
+        check(lib.grasp_ce_loss_bwd(logits.data_ptr(), labels.data_ptr(), coef.data_ptr(), rows, V, loss.data_ptr(),
+                                    _stream()), "grasp_ce_loss_bwd")
+        timers.stop("grasp_rowops", t0, bytes_=8.0 * rows * V)
+    return loss

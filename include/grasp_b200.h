@@ -155,6 +155,61 @@ int    grasp_gemm_f32(int ta, int tb, int64_t M, int64_t N, int64_t K, float alp
                       float beta, float* C, int64_t ldc, int prec,
                       void* ws, size_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * (f1) prepared GEMM operands of the F16X3 arithmetic.  The calibration passes
+ * (modeling_grasp.py:340-354 run the whole model per sample) multiply one
+ * weight by every micro-batch, forward as [N][K] and backward as [K][N], and one
+ * activation by several weights; the split pre-pass is therefore callable on
+ * its own and its result reusable:
+ *   planes  [2][rows][round8(cols)] fp16 (hi, lo) of src * scale, in the STORED
+ *           orientation, grasp_gemm_planes_bytes() bytes, 1024-byte aligned
+ *   inv     inverse scales: GRASP_SCALE_ROWS   -> [rows], one power of two per row
+ *                           GRASP_SCALE_TENSOR -> [max(rows,cols) + 1] floats, one
+ *                           power of two for the whole tensor (last word scratch);
+ *                           valid as A, as B [N][K] and as B [K][N]
+ * grasp_gemm_f16x3_planes: C[M,N] = alpha * A * op(B) + beta * C with
+ *   A planes [2][M][Kp] (row or tensor scale), B planes [2][N][Kp] (b_kn = 0,
+ *   row or tensor scale) or [2][K][Np] (b_kn = 1, tensor scale only).
+ * ------------------------------------------------------------------------- */
+#define GRASP_SCALE_ROWS   0
+#define GRASP_SCALE_TENSOR 2
+size_t grasp_gemm_planes_bytes(int64_t rows, int64_t cols);
+int    grasp_gemm_split_f16(const float* src, int64_t ld, int64_t rows, int64_t cols, int scale_mode,
+                            void* planes, float* inv, void* stream);
+int    grasp_gemm_f16x3_planes(int64_t M, int64_t N, int64_t K, float alpha,
+                               const void* A_planes, const float* inv_a,
+                               const void* B_planes, int b_kn, const float* inv_b,
+                               float beta, float* C, int64_t ldc, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * (f1) row-wise pieces of the LLaMA decoder layer the calibration passes run
+ * between the GEMMs (the reference leaves them to transformers' eager modules,
+ * modeling_grasp.py:347 -> LlamaDecoderLayer.forward: ~25 elementwise launches
+ * per layer).  fp32, row-major, contiguous rows of length d unless a stride is
+ * given.  Each backward is the exact derivative of its forward.
+ *   rmsnorm : y = x * rsqrt(mean(x^2) + eps) * w ; rstd[t] kept for backward
+ *             bwd: dx = rstd * (g - x * rstd^2 * mean(g * x)) (+ add), g = dy * w
+ *   rope    : in place on x [tokens][heads][hd] (token t has position t % seq):
+ *             (x1, x2) -> (x1 c1 - x2 s1, x2 c2 + x1 s2), c/s rows of cos/sin [seq][hd]
+ *             (batch stride cs_batch elements, 0 = shared); inverse != 0 applies the
+ *             transpose (the backward)
+ *   swiglu  : h = silu(g) * u ; bwd: dg = dh * u * s(g) (1 + g (1 - s(g))), du = dh * silu(g)
+ *   ce_loss : per row t of logits [rows][V]: loss[t] = coef[t] * (lse_t - logit[t, label_t]),
+ *             logits overwritten by dloss/dlogits = coef[t] * (softmax - onehot);
+ *             label < 0 -> loss 0, gradient 0 (ignore_index)
+ * ------------------------------------------------------------------------- */
+int grasp_rmsnorm_fwd(const float* x, const float* w, int64_t rows, int64_t d, float eps,
+                      float* y, float* rstd, void* stream);
+int grasp_rmsnorm_bwd(const float* dy, const float* x, const float* w, const float* rstd,
+                      const float* add, int64_t rows, int64_t d, float* dx, void* stream);
+int grasp_rope_inplace(float* x, int64_t tokens, int64_t seq, int64_t heads, int64_t hd,
+                       const float* cos, const float* sin, int64_t cs_batch, int inverse, void* stream);
+int grasp_swiglu_fwd(const float* g, const float* u, int64_t n, float* h, void* stream);
+int grasp_swiglu_bwd(const float* dh, const float* g, const float* u, int64_t n,
+                     float* dg, float* du, void* stream);
+int grasp_ce_loss_bwd(float* logits, const int64_t* labels, const float* coef, int64_t rows, int64_t V,
+                      float* loss, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

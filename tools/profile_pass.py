@@ -23,3 +23,11 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     gm.get_svdlayer_gradients(dl, dev)
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=22, max_name_column_width=70))
+# ---- the layer-scoring forward (stage 1) on the same model
+gm2 = GRASPModel(synth.random_llama("llama2-7b", seed=0, device=dev, num_hidden_layers=4)); gm2.micro_batch = 8
+gm2.compute_bi(num_prune_layers=1, calibration_dataloader=dl, device=dev)
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    gm2.compute_bi(num_prune_layers=1, calibration_dataloader=dl, device=dev)
+    torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=18, max_name_column_width=70))
