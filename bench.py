@@ -262,7 +262,10 @@ def run_ours(a):
         wdl = synth.calibration_dataloader(0, 0, 0, tokens=wtok)
         gm.compute_bi(num_prune_layers=1, calibration_dataloader=wdl, device=dev)
         gm._runner, gm._calib = None, None
+    import gc
+    gc.collect()
     torch.cuda.empty_cache()
+    torch.cuda.reset_peak_memory_stats()
 
     # ---- timed region: the public API call with host-resident tokens
     timer = StageTimer()
@@ -332,7 +335,10 @@ def run_ours(a):
                            "stages_ms": {k: round(v, 2) for k, v in stages.items()}, "end_to_end_s": total_ms / 1e3},
                 "e2e": {"value": n_mat / (total_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d // a.steps,
                         "d2h_bytes_per_step": d2h // a.steps},
-                "gpu_launches": int(launches), "clocks": clk, "roofline": roof}
+                "gpu_launches": int(launches), "clocks": clk, "roofline": roof,
+                "memory": {"peak_allocated_gb": round(torch.cuda.max_memory_allocated() / 2**30, 1),
+                           "peak_reserved_gb": round(torch.cuda.max_memory_reserved() / 2**30, 1),
+                           "alloc_retries": torch.cuda.memory_stats().get("num_alloc_retries", 0)}}
         if not a.no_cpu_baseline and world == 1:
             sample, cpu_total = cpu_reference_sample(a, os.cpu_count() or 1)
             line["cpu_baseline"] = {"value": MATRICES_PER_LAYER * a.steps / cpu_total, "unit": UNIT,

@@ -343,6 +343,261 @@ svd_evd_kernel(SvdGroup g, int round, int sweep, float tol, int inner_cap) {
 }
 
 // ---------------------------------------------------------------------------
+// evd, register-resident variant used by the tensor-core phase (fp32 eigenvectors, same rotations,
+// thresholds and outputs as svd_evd_kernel<float>).
+//
+// svd_evd_kernel spends ~480 warp instructions per Jacobi step on each of 32 warps (index arithmetic,
+// shared-memory round trips, two block barriers for one 2x2 update per thread): ncu shows it issue-bound
+// (39 M warp instructions per launch at n = 4096).  Here the matrices stay in registers for the whole sweep:
+//   lane k of every warp owns columns A = top[k], B = bot[k]
+//   warps 0-3 (G): row slots T[8w..8w+7], B[8w..8w+7] of G           (32 registers)
+//   warps 4-7 (E): rows 8w'..8w'+7 and 32+8w'..32+8w'+7 of E         (32 registers; rows of E never move)
+// Rows live in fixed slots and pair j is always (T[j], B[j]), so every register index is a compile-time
+// constant.  After each step rows and columns move one place round the Brent-Luk ring (T[0] fixed,
+// T[1]..T[31] -> B[31]..B[0] -> T[1]): columns by one warp shuffle per value, rows by the choice of the
+// destination register, the two slots that cross a warp boundary through shared memory.  One step is
+// ~320 instructions on a G warp and two 256-thread barriers; a launch executes ~5x fewer instructions.
+// grid (npairs, nmat), 256 threads.
+// ---------------------------------------------------------------------------
+constexpr int EVW_THREADS = 256;
+
+struct EvdWarpSmem {
+  float G[JS][JS + 1];
+  float E[JS][JS + 1];
+  float c[32], s[32];
+  float xT[4][2][32];     // slot T[8w+7] of G warp w after the column move (-> T[8w+8])
+  float xB[4][2][32];     // slot B[8w]                                     (-> B[8w-1])
+  float red[EVW_THREADS / 32];
+  int rank[JS];
+  int inv[JS];
+  int rotated;
+  int nonident;
+};
+
+// one value pair (column A, column B of this lane) moves to its place for the next step
+__device__ __forceinline__ void ring_cols(float vA, float vB, int lane, float& nA, float& nB) {
+  const float x = (lane == 0) ? vB : vA;
+  const float u = __shfl_up_sync(0xffffffffu, x, 1);
+  const float d = __shfl_down_sync(0xffffffffu, vB, 1);
+  nA = (lane == 0) ? vA : u;
+  nB = (lane == 31) ? vA : d;
+}
+
+__global__ void __launch_bounds__(EVW_THREADS)
+svd_evd_warp_kernel(SvdGroup g, int round, int sweep, float tol, int inner_cap) {
+  const SvdMat& M = g.mat[blockIdx.y];
+  if (M.stats[0]) return;
+  __shared__ EvdWarpSmem sm;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int pair = blockIdx.x;
+  constexpr int H = JS / 2;
+  constexpr int R = 8;                 // row slots of each kind per G warp
+  static_assert(JS == 64, "the register layout assumes 64-row pairs");
+
+  const float* gp = M.Gpart + (int64_t)pair * g.nsplit * (JS * JS);
+  for (int e = tid; e < JS * JS; e += EVW_THREADS) {
+    float v = 0.f;
+#pragma unroll 4
+    for (int sp = 0; sp < g.nsplit; ++sp) v += gp[(int64_t)sp * (JS * JS) + e];
+    sm.G[e / JS][e % JS] = v;
+    sm.E[e / JS][e % JS] = (e / JS == e % JS) ? 1.f : 0.f;
+  }
+  if (tid == 0) { sm.rotated = 0; sm.nonident = 0; }
+  __syncthreads();
+  float maxoff = 0.f;
+  for (int e = tid; e < JS * JS; e += EVW_THREADS) {
+    const int i = e / JS, j = e % JS;
+    if (i < j) {
+      const float v = 0.5f * (sm.G[i][j] + sm.G[j][i]);
+      sm.G[i][j] = v;
+      sm.G[j][i] = v;
+      const float d = sm.G[i][i] * sm.G[j][j];
+      if (d > 0.f) maxoff = fmaxf(maxoff, fabsf(v) * rsqrtf(d));
+    }
+  }
+  maxoff = warp_max(maxoff);
+  if (lane == 0) sm.red[warp] = maxoff;
+  __syncthreads();
+  maxoff = 0.f;
+#pragma unroll
+  for (int i = 0; i < EVW_THREADS / 32; ++i) maxoff = fmaxf(maxoff, sm.red[i]);
+  if (tid == 0) atomicMax(&M.stats[8 + sweep], __float_as_uint(maxoff));
+
+  if (maxoff >= tol) {
+    const bool gw = warp < 4;            // G warp (else E warp)
+    const int w = warp & 3;
+    // G warps: [local slot] of column A / column B, t = slots T[8w + i], b = slots B[8w + i]
+    // E warps: t = rows 8w + i, b = rows 32 + 8w + i
+    float tA[R], tB[R], bA[R], bB[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const int j = 8 * w + i;
+      if (gw) {
+        tA[i] = sm.G[j][lane]; tB[i] = sm.G[j][H + lane];
+        bA[i] = sm.G[H + j][lane]; bB[i] = sm.G[H + j][H + lane];
+      } else {
+        tA[i] = (j == lane) ? 1.f : 0.f; tB[i] = 0.f;
+        bA[i] = 0.f; bB[i] = (j == lane) ? 1.f : 0.f;
+      }
+    }
+    for (int isw = 0; isw < inner_cap; ++isw) {
+      bool rotated = false;
+      for (int t = 0; t < JS - 1; ++t) {
+        // ---- A: the G warp that holds pair k's diagonal block (slot k, lane k) computes its rotation
+        if (gw && (lane >> 3) == w) {
+          float gpp = 0.f, gqq = 0.f, gpq = 0.f;
+#pragma unroll
+          for (int i = 0; i < R; ++i)
+            if (i == (lane & 7)) { gpp = tA[i]; gpq = tB[i]; gqq = bB[i]; }
+          float c = 1.f, s = 0.f;
+          if (gpq != 0.f && gpq * gpq > tol * tol * fabsf(gpp * gqq)) {
+            const float d = gqq - gpp, x = 2.f * gpq;
+            const float tt = x / (d + copysignf(sqrtf(fmaf(d, d, x * x)), d));
+            c = rsqrtf(fmaf(tt, tt, 1.f));
+            s = tt * c;
+            const float h = -0.5f * fmaf(s, s, fmaf(c, c, -1.0f));   // unbiased normalisation (see svd_evd_kernel)
+            c = fmaf(c, h, c);
+            s = fmaf(s, h, s);
+            rotated = true;
+          }
+          sm.c[lane] = c;
+          sm.s[lane] = s;
+        }
+        __syncthreads();
+        // ---- B: rotate, move the columns, shift the row slots
+        const float c = sm.c[lane], s = sm.s[lane];
+        if (gw) {
+          if (s != 0.f) {                                   // G <- G J: this lane's two columns
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+              float a = tA[i], b = tB[i];
+              tA[i] = c * a - s * b; tB[i] = s * a + c * b;
+              a = bA[i]; b = bB[i];
+              bA[i] = c * a - s * b; bB[i] = s * a + c * b;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < R; ++i) {                     // G <- J^T G: row pair 8w + i with the rotation of that lane
+            const float cj = __shfl_sync(0xffffffffu, c, 8 * w + i), sj = __shfl_sync(0xffffffffu, s, 8 * w + i);
+            float a = tA[i], b = bA[i];
+            tA[i] = cj * a - sj * b; bA[i] = sj * a + cj * b;
+            a = tB[i]; b = bB[i];
+            tB[i] = cj * a - sj * b; bB[i] = sj * a + cj * b;
+          }
+          if (s != 0.f && (lane >> 3) == w) {
+#pragma unroll
+            for (int i = 0; i < R; ++i)
+              if (i == (lane & 7)) { tB[i] = 0.f; bA[i] = 0.f; }     // the annihilated pivot, exactly
+          }
+          // column move of every slot, then the slot shift: T[j] <- T[j-1], B[j] <- B[j+1]
+          float oA, oB;
+          ring_cols(tA[R - 1], tB[R - 1], lane, oA, oB);            // T[8w+7] leaves for T[8w+8] (or B[31])
+          sm.xT[w][0][lane] = oA; sm.xT[w][1][lane] = oB;
+          float fA, fB;
+          ring_cols(bA[0], bB[0], lane, fA, fB);                    // B[8w] leaves for B[8w-1] (or T[1])
+          sm.xB[w][0][lane] = fA; sm.xB[w][1][lane] = fB;
+#pragma unroll
+          for (int i = R - 1; i >= 2; --i) ring_cols(tA[i - 1], tB[i - 1], lane, tA[i], tB[i]);
+          {
+            float zA, zB;
+            ring_cols(tA[0], tB[0], lane, zA, zB);                  // old local T[0]
+            if (w == 0) { tA[1] = fA; tB[1] = fB; tA[0] = zA; tB[0] = zB; }   // T[1] <- B[0]; T[0] stays
+            else { tA[1] = zA; tB[1] = zB; }                        // T[8w+1] <- T[8w]; T[8w] is imported below
+          }
+#pragma unroll
+          for (int i = 0; i < R - 1; ++i) ring_cols(bA[i + 1], bB[i + 1], lane, bA[i], bB[i]);
+          if (w == 3) { bA[R - 1] = oA; bB[R - 1] = oB; }           // B[31] <- T[31]
+        } else {
+#pragma unroll
+          for (int i = 0; i < R; ++i) {                     // E <- E J, then the same column move
+            float a = tA[i], b = tB[i];
+            if (s != 0.f) { const float na = c * a - s * b; b = s * a + c * b; a = na; }
+            ring_cols(a, b, lane, tA[i], tB[i]);
+            a = bA[i]; b = bB[i];
+            if (s != 0.f) { const float na = c * a - s * b; b = s * a + c * b; a = na; }
+            ring_cols(a, b, lane, bA[i], bB[i]);
+          }
+        }
+        __syncthreads();
+        // ---- C: the two slots that crossed a warp boundary
+        if (gw) {
+          if (w > 0) { tA[0] = sm.xT[w - 1][0][lane]; tB[0] = sm.xT[w - 1][1][lane]; }
+          if (w < 3) { bA[R - 1] = sm.xB[w + 1][0][lane]; bB[R - 1] = sm.xB[w + 1][1][lane]; }
+        }
+      }
+      // after JS - 1 steps the ring is back where it started: lane k holds columns k and 32 + k again
+      const bool any = __any_sync(0xffffffffu, rotated);
+      if (gw && lane == 0 && any) { sm.rotated = 1; sm.nonident = 1; }
+      __syncthreads();
+      const int again = sm.rotated;
+      __syncthreads();
+      if (tid == 0) sm.rotated = 0;
+      if (!again) break;
+    }
+    if (gw) {
+      if ((lane >> 3) == w) {
+        float dA = 0.f, dB = 0.f;
+#pragma unroll
+        for (int i = 0; i < R; ++i)
+          if (i == (lane & 7)) { dA = tA[i]; dB = bB[i]; }
+        sm.G[lane][lane] = dA;
+        sm.G[H + lane][H + lane] = dB;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        const int j = 8 * w + i;
+        sm.E[j][lane] = tA[i]; sm.E[j][H + lane] = tB[i];
+        sm.E[H + j][lane] = bA[i]; sm.E[H + j][H + lane] = bB[i];
+      }
+    }
+    __syncthreads();
+  }
+
+  // order the new rows by descending squared norm (diag of the rotated Gram)
+  if (tid < JS) {
+    const float di = sm.G[tid][tid];
+    int rk = 0;
+    for (int j = 0; j < JS; ++j) {
+      const float dj = sm.G[j][j];
+      rk += (dj > di) || (dj == di && j < tid);
+    }
+    sm.rank[tid] = rk;
+    if (rk != tid) sm.nonident = 1;
+  }
+  __syncthreads();
+  if (tid < JS) sm.inv[sm.rank[tid]] = tid;
+  __syncthreads();
+  if (tid == 0) M.pair_flag[pair] = sm.nonident;
+  if (M.ETp) {
+    const int ntiles = (g.npairs + 1) / 2;
+    const int64_t plane = (int64_t)ntiles * 128 * 128;
+    __nv_bfloat16* base = M.ETp + ((int64_t)(pair >> 1) * 128 + (pair & 1) * 64) * 128;
+    // two adjacent columns per thread: 4-byte stores, 64 threads cover one 128-column row
+    for (int e = tid; e < JS * 64; e += EVW_THREADS) {
+      const int rn = e >> 6, col = (e & 63) * 2;
+      const int i = col - (pair & 1) * 64;
+      float x0 = 0.f, x1 = 0.f;
+      if (i >= 0 && i < JS) { const int src = sm.inv[rn]; x0 = sm.E[i][src]; x1 = sm.E[i + 1][src]; }
+#pragma unroll
+      for (int pl = 0; pl < 3; ++pl) {
+        const __nv_bfloat16 b0 = __float2bfloat16_rn(x0), b1 = __float2bfloat16_rn(x1);
+        *reinterpret_cast<__nv_bfloat162*>(base + pl * plane + (int64_t)rn * 128 + col) = __halves2bfloat162(b0, b1);
+        x0 -= __bfloat162float(b0);
+        x1 -= __bfloat162float(b1);
+      }
+    }
+  }
+  if (sm.nonident) {
+    float* et = M.ET + (int64_t)pair * (JS * JS);
+    for (int e = tid; e < JS * JS; e += EVW_THREADS) {
+      const int c = e / JS, i = e % JS;
+      et[sm.rank[c] * JS + i] = sm.E[i][c];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // update: Z_pair[:, cols] <- ET (64x64) * Z_pair[:, cols], in place.
 // grid (ldz/128, npairs, nmat); 256 threads, 4 rows x 8 cols per thread.
 // ---------------------------------------------------------------------------
@@ -587,6 +842,8 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
   bool tc_cleanup = false;
   if (const char* e = getenv("GRASP_SVD_TC_CLEANUP")) tc_cleanup = atoi(e) != 0;
   const bool no_cleanup_dbg = getenv("GRASP_SVD_NO_CLEANUP") != nullptr;
+  bool evd_warp = true;   // register-resident 2-warp eigen-solve in the tensor-core phase (0: the 1024-thread kernel)
+  if (const char* e = getenv("GRASP_SVD_EVD_WARP")) evd_warp = atoi(e) != 0;
   if (use_tc) {
     static bool tc_attr = false;
     if (!tc_attr) {
@@ -688,7 +945,10 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
           } else {
             GRASP_LAUNCH(svd_gram_kernel, dim3(g.nsplit, g.npairs, g.nmat), dim3(J_THREADS), 0, st, g, round);
           }
-          if (use_tc && !evd64_dbg)
+          if (use_tc && !evd64_dbg && evd_warp)
+            GRASP_LAUNCH(svd_evd_warp_kernel, dim3(g.npairs, g.nmat), dim3(EVW_THREADS), 0, st, g, round, sweep, tol,
+                         tc_inner_cap);
+          else if (use_tc && !evd64_dbg)
             GRASP_LAUNCH(svd_evd_kernel<float>, dim3(g.npairs, g.nmat), dim3(EVD_THREADS), sizeof(EvdSmem<float>), st, g,
                          round, sweep, tol, tc_inner_cap);
           else

@@ -23,6 +23,7 @@ that lives in tests/ -- the product backend below has no CPU path.
 """
 from __future__ import annotations
 
+import weakref
 from collections import OrderedDict
 from typing import Optional
 
@@ -175,7 +176,9 @@ class FusedLlama:
     """Explicit forward / backward over `runner.layers` (engine.LlamaRunner owns the modules)."""
 
     def __init__(self, runner, backend=None):
-        self.r = runner
+        # the runner owns this object: a proxy avoids a reference cycle that would keep the cached weight
+        # planes (as large as the model) alive until the cycle collector runs
+        self.r = weakref.proxy(runner)
         self.be = backend if backend is not None else CudaBackend()
 
     def supported(self) -> bool:

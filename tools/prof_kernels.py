@@ -17,6 +17,27 @@ elif what == "bi":
     hs = [torch.randn(8, 511, 4096, device=dev) for _ in range(33)]
     acc = torch.zeros(32, dtype=torch.float64, device=dev)
     for _ in range(4): ops.bi_chain(hs, acc)
+elif what == "planes":
+    # the GEMM of the calibration passes at its in-situ shapes (16 samples x 511 tokens), prepared operands
+    from grasp_b200 import _lib
+    T = 8176
+    x = torch.randn(T, 4096, device=dev); w = torch.randn(11008, 4096, device=dev) * 0.02
+    dy = torch.randn(T, 11008, device=dev)
+    for _ in range(2):
+        xo, wo, dyo = ops.split_f16(x), ops.split_f16(w, _lib.SCALE_TENSOR), ops.split_f16(dy)
+        ops.gemm_planes(xo, wo)                 # x W^T   (K-major B)
+        ops.gemm_planes(dyo, wo, b_kn=True)     # dy W    (MN-major B)
+elif what == "rowops":
+    T = 8176
+    x = torch.randn(T, 4096, device=dev); w = torch.ones(4096, device=dev)
+    g = torch.randn(T, 11008, device=dev); u = torch.randn(T, 11008, device=dev)
+    lg = torch.randn(T, 32000, device=dev); lab = torch.randint(0, 32000, (T,), device=dev)
+    cos = torch.randn(1, 511, 128, device=dev); sin = torch.randn(1, 511, 128, device=dev)
+    for _ in range(2):
+        y, r = ops.rmsnorm_fwd(x, w, 1e-5); ops.rmsnorm_bwd(y, x, w, r, add=x)
+        ops.rope_(y, 511, 32, 128, cos, sin)
+        h = ops.swiglu_fwd(g, u); ops.swiglu_bwd(h, g.clone(), u.clone(), inplace=True)
+        ops.ce_loss_bwd_(lg.clone(), lab, torch.ones(T, device=dev))
 elif what == "svd":
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
     A = torch.randn(n, n, device=dev) * 0.02
