@@ -312,8 +312,16 @@ def run_ours(a):
             tag, rec = max((gemm_tags or kt).items(), key=lambda kv: kv[1]["ms"])
             peak = peaks.get("bf16_tflops_sustained", 1400.0)
             achieved = rec["flops"] / (rec["ms"] * 1e-3) / 1e12
+            traffic, traffic_note = None, None
+            try:
+                tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))["tc_gemm_kernel"]
+                traffic = tr["dram_read_bytes"] + tr["dram_write_bytes"]
+                traffic_note = ("ncu dram__bytes_read+write of ONE launch, %s (algorithmic %d bytes); the run's launches "
+                                "mix shapes, see profiles/r01_ncu_traffic.json") % (tr["launch"], tr["algorithmic_bytes"])
+            except (OSError, KeyError, ValueError):
+                pass
             roof = {"bound": "tensor", "kernel": tag, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": None,
+                    "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
                     "launches": rec["n"], "avg_launch_ms": rec["ms"] / max(rec["n"], 1),
                     "issued_mma_tflops": achieved * rec["mma_per_flop"],

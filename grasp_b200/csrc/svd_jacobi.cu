@@ -714,6 +714,32 @@ __global__ void svd_emit_cols_kernel(const float* __restrict__ Z, int ldz, int c
   }
 }
 
+// convergence check on the full Gram T = Y Y^T (one tensor-core GEMM) instead of a verification sweep:
+// stats[60] = bits of max_{i != j} |t_ij| / sqrt(t_ii t_jj); grid = rows
+__global__ void __launch_bounds__(256)
+svd_offdiag_max_kernel(const float* __restrict__ T, int ld, int r, uint32_t* __restrict__ stats) {
+  if (stats[0]) return;
+  const int i = blockIdx.x;
+  const float dii = T[(int64_t)i * ld + i];
+  float m = 0.f;
+  for (int j = threadIdx.x; j < r; j += blockDim.x) {
+    if (j == i) continue;
+    const float d = dii * T[(int64_t)j * ld + j];
+    if (d > 0.f) m = fmaxf(m, fabsf(T[(int64_t)i * ld + j]) * rsqrtf(d));
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(&stats[60], __float_as_uint(m));
+}
+
+__global__ void svd_check_end_kernel(SvdGroup g, float tol) {
+  const int m = threadIdx.x;
+  if (m >= g.nmat) return;
+  uint32_t* st = g.mat[m].stats;
+  if (st[0]) return;
+  if (__uint_as_float(st[60]) < tol) { st[0] = 1; st[2] = st[60]; }
+  st[60] = 0;
+}
+
 __global__ void svd_reopen_kernel(SvdGroup g) {
   if (threadIdx.x < g.nmat) {
     uint32_t* st = g.mat[threadIdx.x].stats;
@@ -775,6 +801,8 @@ static SvdPlan make_plan(int64_t m, int64_t n) {
   P.off_T = o;     o = align_up(o + (size_t)P.rp * P.rp * 4, 1024);
   size_t g1 = tc_gemm_workspace_bytes(P.rp, P.rp, P.rp, GRASP_PREC_BF16X6);
   size_t g2 = tc_gemm_workspace_bytes(P.rp, P.L, P.r, GRASP_PREC_BF16X6);
+  const size_t g3 = tc_gemm_workspace_bytes(P.rp, P.rp, P.Lp, GRASP_PREC_F16X3);   // convergence check Y Y^T
+  if (g3 > g2) g2 = g3;
   P.gws_bytes = align_up(g1 > g2 ? g1 : g2, 1024);
   P.off_gws = o;   o = align_up(o + P.gws_bytes, 1024);
   P.bytes = o;
@@ -842,6 +870,8 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
   bool tc_cleanup = false;
   if (const char* e = getenv("GRASP_SVD_TC_CLEANUP")) tc_cleanup = atoi(e) != 0;
   const bool no_cleanup_dbg = getenv("GRASP_SVD_NO_CLEANUP") != nullptr;
+  bool gemm_check = true;   // confirm convergence of the clean-up with one Gram GEMM instead of a second sweep
+  if (const char* e = getenv("GRASP_SVD_GEMM_CHECK")) gemm_check = atoi(e) != 0;
   bool evd_warp = true;   // register-resident 2-warp eigen-solve in the tensor-core phase (0: the 1024-thread kernel)
   if (const char* e = getenv("GRASP_SVD_EVD_WARP")) evd_warp = atoi(e) != 0;
   if (use_tc) {
@@ -1025,7 +1055,23 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
             }
           }
           GRASP_LAUNCH(svd_sweep_end_kernel, dim3(1), dim3(32), 0, st, g, sweep, cleanup_conv, s2);
+          if (s2 == 0 && !tc_cleanup && gemm_check) {
+            // A sweep only knows the off-diagonals it met BEFORE rotating them, so confirming convergence costs
+            // another full sweep (Gram + eigen-solve of every pair, ~45% of a sweep).  The whole Gram as one
+            // fp32-class tensor-core GEMM plus a max-reduction gives the same answer for ~1 ms per matrix.
+            for (int j = 0; j < g.nmat && !rc; ++j) {
+              const SvdPlan& Q = plans[members[j]];
+              float* T = reinterpret_cast<float*>(base[members[j]] + Q.off_T);
+              rc = tc_gemm_f32(0, 1, Q.rp, Q.rp, Q.Lp, 1.f, g.mat[j].Z, Q.ldz, g.mat[j].Z, Q.ldz, 0.f, T, Q.rp, 0,
+                               GRASP_PREC_F16X3, base[members[j]] + Q.off_gws, Q.gws_bytes, stream);
+              if (rc) break;
+              GRASP_LAUNCH(svd_offdiag_max_kernel, dim3((unsigned)Q.r), dim3(256), 0, st, T, Q.rp, Q.r, g.mat[j].stats);
+            }
+            if (rc) break;
+            GRASP_LAUNCH(svd_check_end_kernel, dim3(1), dim3(32), 0, st, g, cleanup_conv);
+          }
         }
+        if (rc) { delete maps; break; }
         if (tc_cleanup) {
           for (int j = 0; j < g.nmat; ++j) {
             const SvdPlan& Q = plans[members[j]];
