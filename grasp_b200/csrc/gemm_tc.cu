@@ -43,6 +43,7 @@ struct TcParams {
   float* partial;     // EPI_SIGMA: [tiles_m][N]
   const float* inv_sa;  // F16 planes: per-row inverse scale of A (M) and B (N); the accumulator is
   const float* inv_sb;  //   multiplied by inv_sa[m] * inv_sb[n] before the epilogue
+  int kgroup;           // K blocks accumulated in one TMEM buffer before the epilogue drains it (0 = 1)
 };
 
 template <int NS, int BN>
@@ -77,6 +78,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks = (p.K + TC_BK - 1) / TC_BK;
+  // The epilogue reads a whole 128 x BN fp32 accumulator per drain and TMEM reads run at 64 B/clk: at one drain
+  // per 64-wide K block that is 2048 clk against 1536 clk of MMAs (BN = 256, three products), i.e. the kernel is
+  // TMEM-read-bound at ~75 % tensor-pipe activity.  `kgroup` K blocks share one accumulator before it is drained.
+  const int kgroup = p.kgroup > 0 ? p.kgroup : 1;
+  const int kgroups = (kblocks + kgroup - 1) / kgroup;
   const int total_tiles = p.tiles_m * p.tiles_n;
 
   if (warp == 0 && lane == 0) {
@@ -131,8 +137,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int in_group = 0;
         for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+          if (in_group == 0) mbar_wait(&acc_empty[acc], acc_phase ^ 1);
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -148,13 +155,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               // K-major: +32 bytes per 16-element K step inside the 128-byte swizzle row;
               // MN-major: 16 K rows = two 8-row groups = +2048 bytes
               const uint64_t kb_step = BMN ? (uint64_t)(128 * k) : (uint64_t)(2 * k);
-              umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + kb_step, idesc, (q | k) != 0);
+              umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + kb_step, idesc, (in_group | q | k) != 0);
             }
           }
           umma_commit(&empty_bar[stage]);           // frees the smem stage when the MMAs retire
-          umma_commit(&acc_full[acc]);              // this K block's partial product is complete
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+          if (++in_group == kgroup || kb == kblocks - 1) {
+            umma_commit(&acc_full[acc]);            // this group's partial product is complete
+            in_group = 0;
+            if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+          }
         }
       }
     }
@@ -171,7 +181,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       float racc[128];
 #pragma unroll
       for (int j = 0; j < 128; ++j) racc[j] = 0.f;
-      for (int kb = 0; kb < kblocks; ++kb) {
+      for (int grp = 0; grp < kgroups; ++grp) {
         mbar_wait(&acc_full[acc], acc_phase);
         tc_fence_after_sync();
         const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * 128);
@@ -802,6 +812,8 @@ static int split_operand_f16(const float* src, int64_t ld, int layout, int R, in
   return 0;
 }
 
+static int gemm_kgroup(int ns);
+
 template <int NS, int BN, int EPI, int BMN = 0, int F16 = 0>
 static int launch_core(const __nv_bfloat16* Ap, const __nv_bfloat16* Bp, TcParams prm, void* stream) {
   using Cfg = TcCfg<NS, BN>;
@@ -822,6 +834,7 @@ static int launch_core(const __nv_bfloat16* Ap, const __nv_bfloat16* Bp, TcParam
   }
   prm.tiles_m = (int)ceil_div(prm.M, TC_BM);
   prm.tiles_n = (int)ceil_div(prm.N, BN);
+  prm.kgroup = gemm_kgroup(NS);
   const int total = prm.tiles_m * prm.tiles_n;
   const int grid = total < sm_count() ? total : sm_count();
   GRASP_LAUNCH((tc_gemm_kernel<NS, BN, EPI, BMN, F16>), dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, mapA, mapB, prm);
@@ -832,17 +845,35 @@ static int launch_core(const __nv_bfloat16* Ap, const __nv_bfloat16* Bp, TcParam
 // Tile width of the two-plane arithmetics.  The kernel is persistent with static tile assignment, so
 // the cost is (waves of tiles over the SMs) x (time of one tile); a 256-wide tile does twice the work
 // of a 128-wide one in ~1.55x the time (fewer operand bytes per MMA).  GRASP_GEMM_BN forces a width.
-static bool wide_tiles(int64_t M, int64_t N) {
+static bool wide_tiles(int64_t M, int64_t N, int64_t K = 1 << 20) {
   static int forced = -1;
   if (forced < 0) { const char* e = getenv("GRASP_GEMM_BN"); forced = e ? atoi(e) : 0; }
   if (forced == 128) return false;
   if (forced == 256) return N > 128;
   if (N <= 128) return false;
+  // short K (the rank-k factors of compressed layers): a tile lives for a few K blocks only, so the time goes
+  // to its epilogue; 128-wide tiles have a 3-deep operand ring and twice the tiles to balance (measured 8-14 %
+  // faster for K <= 298, N >= 4096: profiles/r01_gemm_tile_width_short_k.txt)
+  if (K <= 512 && N > 256) return false;
   const int64_t sms = sm_count();
   const int64_t tm = ceil_div(M, TC_BM);
   const double c128 = (double)ceil_div(tm * ceil_div(N, 128), sms);
   const double c256 = (double)ceil_div(tm * ceil_div(N, 256), sms) * 1.55;
   return c256 < c128;
+}
+
+// K blocks per accumulator drain (see tc_gemm_kernel).  The tensor core adds into its accumulator with
+// truncation, so longer chains drift towards zero.  Measured on B200 (tools/gemm_kgroup_check.py, K = 4096,
+// operands with a non-zero mean): 1 block per drain 5.0e-7 max / -1.0e-7 mean signed error at 0.670 ms
+// (8176 x 4096 x 4096), 2 blocks 6.1e-7 / -3.2e-7 at 0.652 ms, 4 blocks 9.8e-7 / -7.5e-7 at 0.638 ms,
+// 8 blocks 1.9e-6 / -1.6e-6 at 0.634 ms (torch fp32 matmul: 3.5e-6, unbiased).  The drain is therefore NOT what
+// limits the kernel (3-5 %): at 410-430 TFLOP/s fp32-equivalent = 1.25-1.3 PFLOP/s of fp16 MMA it runs at the
+// power-capped sustained rate of the part.  Default 1 (accuracy first); GRASP_GEMM_KGROUP overrides.
+static int gemm_kgroup(int ns) {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GRASP_GEMM_KGROUP"); v = e ? atoi(e) : 0; }
+  (void)ns;
+  return v > 0 ? v : 1;
 }
 
 static bool use_bmn() {
@@ -928,7 +959,7 @@ int tc_gemm_f32(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, co
       if (bmn) return launch_core2<EPI_STORE, 1, 1>(Ap, Bp, prm, stream);
       return launch_core2<EPI_STORE, 0, 1>(Ap, Bp, prm, stream);
     }
-    if (wide_tiles(M, N)) {
+    if (wide_tiles(M, N, K)) {
       if (bmn) return launch_core<2, 256, EPI_STORE, 1, 1>(Ap, Bp, prm, stream);
       return launch_core<2, 256, EPI_STORE, 0, 1>(Ap, Bp, prm, stream);
     }
@@ -1106,7 +1137,7 @@ int tc_gemm_planes(int64_t M, int64_t N, int64_t K, float alpha, const void* Ap,
     if (b_kn) return launch_core2<EPI_STORE, 1, 1>(A16, B16, prm, stream);
     return launch_core2<EPI_STORE, 0, 1>(A16, B16, prm, stream);
   }
-  if (wide_tiles(M, N)) {
+  if (wide_tiles(M, N, K)) {
     if (b_kn) return launch_core<2, 256, EPI_STORE, 1, 1>(A16, B16, prm, stream);
     return launch_core<2, 256, EPI_STORE, 0, 1>(A16, B16, prm, stream);
   }
