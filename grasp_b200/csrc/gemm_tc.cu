@@ -555,8 +555,8 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16* out) {
 template <int NS>
 __global__ void split_rows_kernel(const float* __restrict__ src, int64_t ld, int R, int K, int Kp,
                                   __nv_bfloat16* __restrict__ planes) {
-  const int r = blockIdx.y;
-  const int k0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int r = blockIdx.x;                                   // rows on grid.x (may exceed 65535)
+  const int k0 = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
   if (k0 >= Kp) return;
   float x[4];
   const float* s = src + (int64_t)r * ld + k0;
@@ -630,6 +630,26 @@ __global__ void rowmax_scale_kernel(const float* __restrict__ src, int64_t ld, i
   if ((threadIdx.x & 31) == 0) scale_from_max(m, scale[r], inv[r]);
 }
 
+// inv[r] only (long rows: the split kernel recovers the scale as 1 / inv)
+__global__ void rowmax_inv_kernel(const float* __restrict__ src, int64_t ld, int R, int K, float* __restrict__ inv) {
+  const int r = blockIdx.x;
+  if (r >= R) return;
+  __shared__ float red[8];
+  const float* row = src + (int64_t)r * ld;
+  float m = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) m = fmaxf(m, fabsf(row[k]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    float s, i2;
+    scale_from_max(m, s, i2);
+    inv[r] = i2;
+  }
+}
+
 // scale[c], inv[c] from max_r |src[r*ld + c]|  (32 columns per block, coalesced rows)
 __global__ void colmax_scale_kernel(const float* __restrict__ src, int64_t ld, int R, int Ccols, float* __restrict__ scale,
                                     float* __restrict__ inv) {
@@ -657,12 +677,12 @@ __device__ __forceinline__ void split_f16(float x, uint16_t& hi, uint16_t& lo) {
 // planes[pl][r][k] = part_pl(src[r*ld + k] * rs[r] * cs[k]); rs / cs nullable (exactly one is used)
 __global__ void split_rows_f16_kernel(const float* __restrict__ src, int64_t ld, int R, int K, int Kp,
                                       const float* __restrict__ rs, const float* __restrict__ cs,
-                                      uint16_t* __restrict__ planes) {
-  const int r = blockIdx.y;
-  const int k0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+                                      uint16_t* __restrict__ planes, int rs_inverted = 0) {
+  const int r = blockIdx.x;                                   // rows on grid.x (may exceed 65535)
+  const int k0 = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
   if (k0 >= Kp) return;
   const float* srow = src + (int64_t)r * ld + k0;
-  const float sr = rs ? rs[r] : 1.f;
+  const float sr = rs ? (rs_inverted ? 1.f / rs[r] : rs[r]) : 1.f;   // powers of two: the reciprocal is exact
   uint16_t hi[4], lo[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -775,7 +795,7 @@ template <int NS>
 static int split_operand(const float* src, int64_t ld, int transposed, int R, int K, __nv_bfloat16* planes, void* stream) {
   const int Kp = kp_of(K);
   if (!transposed) {
-    dim3 grid((unsigned)ceil_div(Kp, 4 * 256), (unsigned)R);
+    dim3 grid((unsigned)R, (unsigned)ceil_div(Kp, 4 * 256));
     GRASP_LAUNCH((split_rows_kernel<NS>), grid, dim3(256), 0, stream, src, ld, R, K, Kp, planes);
   } else {
     dim3 grid((unsigned)ceil_div(Kp, 32), (unsigned)ceil_div(R, 32));
@@ -795,7 +815,7 @@ static int split_operand_f16(const float* src, int64_t ld, int layout, int R, in
   if (layout == 0) {
     const int Kp = kp_of(K);
     GRASP_LAUNCH(rowmax_scale_kernel, dim3((unsigned)ceil_div(R, 8)), dim3(256), 0, stream, src, ld, R, K, scale, inv);
-    GRASP_LAUNCH(split_rows_f16_kernel, dim3((unsigned)ceil_div(Kp, 4 * 256), (unsigned)R), dim3(256), 0, stream, src,
+    GRASP_LAUNCH(split_rows_f16_kernel, dim3((unsigned)R, (unsigned)ceil_div(Kp, 4 * 256)), dim3(256), 0, stream, src,
                  ld, R, K, Kp, (const float*)scale, (const float*)nullptr, pl);
   } else if (layout == 1) {
     const int Kp = kp_of(K);
@@ -805,7 +825,7 @@ static int split_operand_f16(const float* src, int64_t ld, int layout, int R, in
   } else {
     const int Rp = kp_of(R);
     GRASP_LAUNCH(colmax_scale_kernel, dim3((unsigned)ceil_div(R, 32)), dim3(32, 8), 0, stream, src, ld, K, R, scale, inv);
-    GRASP_LAUNCH(split_rows_f16_kernel, dim3((unsigned)ceil_div(Rp, 4 * 256), (unsigned)K), dim3(256), 0, stream, src,
+    GRASP_LAUNCH(split_rows_f16_kernel, dim3((unsigned)K, (unsigned)ceil_div(Rp, 4 * 256)), dim3(256), 0, stream, src,
                  ld, K, R, Rp, (const float*)nullptr, (const float*)scale, pl);
   }
   GRASP_CHECK_LAST("fp16 split kernels");
@@ -1068,10 +1088,10 @@ __global__ void tensorsplit_f16_kernel(const float* __restrict__ src, int64_t ld
                                        float* __restrict__ inv, int n_inv) {
   float s, i;
   scale_from_max(__uint_as_float(*maxbits), s, i);
-  const int r = blockIdx.y;
-  const int k0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int r = blockIdx.x;                                   // rows on grid.x: vocabularies exceed 65535 rows
+  const int k0 = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
   if (r == 0)
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_inv; j += gridDim.x * blockDim.x) inv[j] = i;
+    for (int j = blockIdx.y * blockDim.x + threadIdx.x; j < n_inv; j += gridDim.y * blockDim.x) inv[j] = i;
   if (k0 >= Kp) return;
   const float* srow = src + (int64_t)r * ld + k0;
   uint16_t hi[4], lo[4];
@@ -1095,7 +1115,14 @@ int tc_split_f16(const float* src, int64_t ld, int64_t rows, int64_t cols, int s
   uint16_t* pl = static_cast<uint16_t*>(planes);
   if (scale_mode == GRASP_SCALE_ROWS) {
     const size_t smem = (size_t)Kp * 4;
-    if (smem > 200 * 1024) return bad_arg("split: row longer than 51200 elements");
+    if (smem > 200 * 1024) {
+      // rows that do not fit in shared memory (logits of a 128k vocabulary): maximum and split as two passes
+      GRASP_LAUNCH(rowmax_inv_kernel, dim3((unsigned)R), dim3(256), 0, stream, src, ld, R, K, inv);
+      GRASP_LAUNCH(split_rows_f16_kernel, dim3((unsigned)R, (unsigned)ceil_div(Kp, 4 * 256)), dim3(256), 0, stream, src,
+                   ld, R, K, Kp, (const float*)inv, (const float*)nullptr, pl, 1);
+      GRASP_CHECK_LAST("long-row split kernels");
+      return 0;
+    }
     static size_t attr = 48 * 1024;
     if (smem > attr) {
       int rc = check_cuda(cudaFuncSetAttribute(rowsplit_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
@@ -1114,7 +1141,7 @@ int tc_split_f16(const float* src, int64_t ld, int64_t rows, int64_t cols, int s
   int rc = check_cuda(cudaMemsetAsync(maxbits, 0, 4, (cudaStream_t)stream), "split memset");
   if (rc) return rc;
   GRASP_LAUNCH(absmax_bits_kernel, dim3((unsigned)(R < 1184 ? R : 1184)), dim3(256), 0, stream, src, ld, R, K, maxbits);
-  GRASP_LAUNCH(tensorsplit_f16_kernel, dim3((unsigned)ceil_div(Kp, 4 * 256), (unsigned)R), dim3(256), 0, stream, src, ld,
+  GRASP_LAUNCH(tensorsplit_f16_kernel, dim3((unsigned)R, (unsigned)ceil_div(Kp, 4 * 256)), dim3(256), 0, stream, src, ld,
                R, K, Kp, (const uint32_t*)maxbits, pl, inv, n_inv);
   GRASP_CHECK_LAST("tensor split kernels");
   return 0;

@@ -37,6 +37,23 @@ def test_gemm_planes_forward_and_backward_forms(cuda, M, N, K):
         ops.gemm_planes(dyo, wr, b_kn=True)      # a [K, N] operand needs one scale for the whole tensor
 
 
+def test_operands_with_more_than_65535_rows(cuda):
+    """lm_head of a 128k-token vocabulary: the row index must not sit on a 16-bit grid dimension."""
+    from grasp_b200 import _lib, ops
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(96, 72, generator=g).to(cuda)
+    w = torch.randn(70001, 72, generator=g).to(cuda)
+    ref = x.double() @ w.double().t()
+    xo = ops.split_f16(x)
+    assert rel(ops.gemm_planes(xo, ops.split_f16(w, _lib.SCALE_TENSOR)), ref) < 2e-6
+    assert rel(ops.gemm_planes(xo, ops.split_f16(w, _lib.SCALE_ROWS)), ref) < 2e-6
+    assert rel(ops.gemm(x, w, tb=True), ref) < 2e-6                       # split inside grasp_gemm_f32
+    dy = torch.randn(96, 70001, generator=g).to(cuda)
+    assert rel(ops.gemm_planes(ops.split_f16(dy), ops.split_f16(w, _lib.SCALE_TENSOR), b_kn=True),
+               dy.double() @ w.double()) < 2e-6
+    assert rel(ops.gemm(dy, w), dy.double() @ w.double()) < 2e-6
+
+
 def test_split_scales_badly_scaled_rows_and_zero_rows(cuda):
     from grasp_b200 import _lib, ops
     g = torch.Generator().manual_seed(5)
