@@ -166,25 +166,29 @@ def run_reference(a):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    times = []
-    sample = None
-    for i in range(a.warmup + a.steps):
+    # every iteration times the same bounded sample and extrapolates it to the K-layer job; the number of
+    # iterations is cut so that the arm ends within a few minutes (the job itself stays the K-layer one)
+    times, sample, budget_s = [], None, 240.0
+    planned = a.warmup + a.steps
+    for i in range(planned):
         t0 = time.perf_counter()
         sample, total = cpu_reference_sample(a, threads)
         dt = time.perf_counter() - t0
-        if i >= a.warmup:
-            times.append((dt, total))
-        if i == 0 and dt * (a.warmup + a.steps) > 240:     # keep the arm within a few minutes
-            a.steps, a.warmup = max(1, min(a.steps, int(180 / dt))), 0
-            times = [(dt, total)]
+        if i >= a.warmup or i == planned - 1:
+            times.append(total)
+        if i == 0 and dt * planned > budget_s:
+            planned = max(1, int(budget_s / dt))
+            if planned <= a.warmup:                # no room for untimed iterations: keep what was measured
+                times = [total]
+        if i + 1 >= planned:
             break
-    total = statistics.median(t for _, t in times)
+    total = statistics.median(times)
     value = MATRICES_PER_LAYER * a.steps / total
-    desc = ("per step: torch.linalg.svd of one %dx%d fp32 matrix + 1 calibration sample (dense forward of one layer "
+    desc = ("per iteration: torch.linalg.svd of one %dx%d fp32 matrix + 1 calibration sample (dense forward of one layer "
             "+ reference GRASPLayer attention-block forward/backward) on a 1-layer model of the named widths; "
             "whole job extrapolated: 4+3x(MLP flop ratio) SVDs per layer, 2 passes x %d samples x (31 dense layer "
-            "forwards + block pass), BI forward of every sample") % (
-                a.cpu_svd_dim or 4096, a.cpu_svd_dim or 4096, a.samples)
+            "forwards + block pass), BI forward of every sample; %d timed iteration(s), median") % (
+                a.cpu_svd_dim or 4096, a.cpu_svd_dim or 4096, a.samples, len(times))
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1000.0 * total / a.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",

@@ -69,3 +69,14 @@ def test_cache_from_checkpoint_matches_cache_from_scratch():
     runner.cache = {}
     runner.build_cache(calib, [1])                                       # no usable checkpoint: from the embeddings
     assert torch.allclose(runner.cache[1], states[1], atol=1e-5)
+
+
+def test_perplexity_evaluator_matches_reference_formula():
+    """grasp_b200.evaluate.evaluate_perplexity == reference evaluate_grasp.py:99-127 (oracle restatement)."""
+    from grasp_b200 import evaluate
+    from oracle import restate
+    model = synth.random_llama("tiny", seed=3)
+    tok = synth.random_tokens(5, 20, 256, seed=2)
+    ref = restate.perplexity(model, tok)
+    assert abs(evaluate.evaluate_perplexity(model, tok, None, "cpu", micro_batch=2) - ref) / ref < 1e-5
+    assert abs(evaluate.evaluate_perplexity(model, tok, 2, "cpu") - restate.perplexity(model, tok[:2])) / ref < 1e-5

@@ -212,3 +212,26 @@ def test_weight_plane_cache_follows_module_replacement(cuda):
         w.mul_(2.0)                                       # an in-place change bumps the version: planes are redone
     assert f.be.wprep(w, 0) is not op
     assert isinstance(f.be, fz.CudaBackend)
+
+
+def test_perplexity_evaluator_on_the_fused_route(cuda):
+    """evaluate_grasp.py:99-127 through the fused forward + grasp_ce_loss_bwd, against the CPU oracle; also on
+    a model whose layers are partly compressed to factor pairs."""
+    import copy
+    from grasp_b200 import evaluate, synth
+    from oracle import restate
+    from modeling_grasp import GRASPModel
+    cpu_model = synth.random_llama("small", seed=2)
+    tok = synth.random_tokens(6, 33, cpu_model.config.vocab_size, seed=5)
+    ref = restate.perplexity(cpu_model, tok)
+    model = copy.deepcopy(cpu_model)
+    got = evaluate.evaluate_perplexity(model, tok, None, cuda, micro_batch=4)
+    assert abs(got - ref) / ref < 1e-4
+    gm = GRASPModel(model)
+    dl = synth.calibration_dataloader(0, 0, 0, tokens=tok)
+    gm.compress_block(4, "mlp", ["down_proj", "up_proj", "gate_proj"], device=cuda)
+    gm.compile_grasp_model(gm.dynamic_svd_selection(gm.get_svdlayer_gradients(dl, cuda), compression_ratio=0.5),
+                           merge=False, device=cuda)
+    got_c = evaluate.evaluate_perplexity(gm, tok, None, cuda)
+    ref_c = restate.perplexity(copy.deepcopy(gm.model).to("cpu"), tok)
+    assert abs(got_c - ref_c) / ref_c < 1e-4
