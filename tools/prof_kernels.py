@@ -38,6 +38,10 @@ elif what == "rowops":
         ops.rope_(y, 511, 32, 128, cos, sin)
         h = ops.swiglu_fwd(g, u); ops.swiglu_bwd(h, g.clone(), u.clone(), inplace=True)
         ops.ce_loss_bwd_(lg.clone(), lab, torch.ones(T, device=dev))
+elif what == "svd4":
+    # one batch of four 4096 x 4096 matrices, two sweeps (what the 7B job's attention projections look like)
+    As = [torch.randn(4096, 4096, device=dev) * 0.02 for _ in range(4)]
+    ops.svd_batched(As, max_sweeps=1)
 elif what == "svd":
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
     A = torch.randn(n, n, device=dev) * 0.02
