@@ -18,6 +18,7 @@
 // the epilogue warps add the block result into fp32 registers with round-to-nearest.  The TMEM
 // buffers form a ring (512 / BN deep), so the MMA warp never waits for the epilogue.
 #include "tc_common.cuh"
+#include "split_f16.cuh"
 #include <stdlib.h>
 
 namespace grasp {
@@ -609,15 +610,6 @@ __global__ void split_transposed_kernel(const float* __restrict__ src, int64_t l
 // fp16 planes: x*s = hi + lo with s a per-row power of two that puts the row maximum in [2^14, 2^15)
 // (fp16 keeps 11 bits, two planes 22; the row scale keeps every row inside fp16's range).
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void scale_from_max(float m, float& s, float& inv) {
-  const int ef = (int)((__float_as_uint(m) >> 23) & 0xffu);     // biased exponent of the row maximum
-  if (ef == 0 || ef == 0xff) { s = 1.f; inv = 1.f; return; }    // zero / denormal / inf / nan row: leave as is
-  int e = 14 - (ef - 127);                                      // s = 2^e
-  e = e > 100 ? 100 : (e < -100 ? -100 : e);
-  s = __uint_as_float((uint32_t)(127 + e) << 23);
-  inv = __uint_as_float((uint32_t)(127 - e) << 23);
-}
-
 // scale[r], inv[r] from max_k |src[r*ld + k]|  (one warp per row)
 __global__ void rowmax_scale_kernel(const float* __restrict__ src, int64_t ld, int R, int K, float* __restrict__ scale,
                                     float* __restrict__ inv) {
@@ -665,13 +657,6 @@ __global__ void colmax_scale_kernel(const float* __restrict__ src, int64_t ld, i
     for (int y = 1; y < 8; ++y) m = fmaxf(m, red[y][threadIdx.x]);
     scale_from_max(m, scale[c], inv[c]);
   }
-}
-
-__device__ __forceinline__ void split_f16(float x, uint16_t& hi, uint16_t& lo) {
-  const __half h = __float2half_rn(x);
-  const __half l = __float2half_rn(x - __half2float(h));
-  hi = __half_as_ushort(h);
-  lo = __half_as_ushort(l);
 }
 
 // planes[pl][r][k] = part_pl(src[r*ld + k] * rs[r] * cs[k]); rs / cs nullable (exactly one is used)
@@ -1019,8 +1004,7 @@ __global__ void __launch_bounds__(256)
 rowsplit_f16_kernel(const float* __restrict__ src, int64_t ld, int R, int K, int Kp, uint16_t* __restrict__ planes,
                     float* __restrict__ inv) {
   extern __shared__ __align__(16) float rowbuf[];     // Kp floats
-  __shared__ float red[8];
-  __shared__ float s_scale;
+  __shared__ float red[9];
   const int r = blockIdx.x;
   const float* row = src + (int64_t)r * ld;
   float m = 0.f;
@@ -1040,35 +1024,7 @@ rowsplit_f16_kernel(const float* __restrict__ src, int64_t ld, int R, int K, int
       m = fmaxf(m, fabsf(v));
     }
   }
-  m = warp_max(m);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    float v = (threadIdx.x < 8) ? red[threadIdx.x] : 0.f;
-    v = warp_max(v);
-    if (threadIdx.x == 0) {
-      float s, i;
-      scale_from_max(v, s, i);
-      s_scale = s;
-      inv[r] = i;
-    }
-  }
-  __syncthreads();
-  const float s = s_scale;
-  uint16_t* d0 = planes + (int64_t)r * Kp;
-  uint16_t* d1 = d0 + (int64_t)R * Kp;
-  for (int k = threadIdx.x * 8; k < Kp; k += 256 * 8) {     // Kp % 8 == 0: 16-byte stores
-    uint16_t hi[8], lo[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) split_f16(rowbuf[k + j] * s, hi[j], lo[j]);
-    uint4 w;
-    w.x = hi[0] | ((uint32_t)hi[1] << 16); w.y = hi[2] | ((uint32_t)hi[3] << 16);
-    w.z = hi[4] | ((uint32_t)hi[5] << 16); w.w = hi[6] | ((uint32_t)hi[7] << 16);
-    *reinterpret_cast<uint4*>(d0 + k) = w;
-    w.x = lo[0] | ((uint32_t)lo[1] << 16); w.y = lo[2] | ((uint32_t)lo[3] << 16);
-    w.z = lo[4] | ((uint32_t)lo[5] << 16); w.w = lo[6] | ((uint32_t)lo[7] << 16);
-    *reinterpret_cast<uint4*>(d1 + k) = w;
-  }
+  block_row_split_256(rowbuf, m, Kp, planes + (int64_t)r * Kp, planes + ((int64_t)R + r) * Kp, inv + r, red);
 }
 
 // bits of max |src| over the whole tensor (non-negative floats order like their bit patterns)

@@ -6,6 +6,7 @@
 // (row staged in shared memory, so every operand is read once and every result written once),
 // 16-byte accesses, fp32 arithmetic.
 #include "common.cuh"
+#include "split_f16.cuh"
 
 namespace grasp {
 
@@ -24,11 +25,14 @@ __device__ __forceinline__ float block_sum_256(float v, float* red /*[8]*/) {
 
 // ------------------------------------------------------------------------------------ RMSNorm
 // y = x * rstd * w, rstd = rsqrt(mean(x^2) + eps)   (transformers LlamaRMSNorm.forward)
+// y (fp32) and/or its GEMM operand form (fp16 hi/lo planes + row scale) are written; the consumer of a norm is
+// always a linear, so the passes usually want only the planes: x is read once and nothing is re-read.
 __global__ void __launch_bounds__(ROW_THREADS)
-rmsnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, int d, float eps, float* __restrict__ y,
-                   float* __restrict__ rstd) {
-  extern __shared__ __align__(16) float rowbuf[];   // d floats
-  __shared__ float red[8];
+rmsnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, int d, int dp, float eps,
+                   float* __restrict__ y, float* __restrict__ rstd, uint16_t* __restrict__ planes,
+                   float* __restrict__ inv, int64_t rows) {
+  extern __shared__ __align__(16) float rowbuf[];   // dp floats (d rounded up to 8)
+  __shared__ float red[9];
   const int64_t r = blockIdx.x;
   const float* xr = x + r * d;
   float ss = 0.f;
@@ -49,17 +53,30 @@ rmsnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, int
   ss = block_sum_256(ss, red);
   const float rs = rsqrtf(ss / (float)d + eps);
   if (threadIdx.x == 0) rstd[r] = rs;
-  float* yr = y + r * d;
+  float* yr = y ? y + r * d : nullptr;
+  float m = 0.f;
   if (vec) {
     for (int k = threadIdx.x * 4; k < d; k += ROW_THREADS * 4) {
       const float4 v = *reinterpret_cast<const float4*>(rowbuf + k);
       const float4 ww = *reinterpret_cast<const float4*>(w + k);
       float4 o;
       o.x = ww.x * (v.x * rs); o.y = ww.y * (v.y * rs); o.z = ww.z * (v.z * rs); o.w = ww.w * (v.w * rs);
-      *reinterpret_cast<float4*>(yr + k) = o;
+      if (yr) *reinterpret_cast<float4*>(yr + k) = o;
+      if (planes) {
+        *reinterpret_cast<float4*>(rowbuf + k) = o;
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
+      }
     }
   } else {
-    for (int k = threadIdx.x; k < d; k += ROW_THREADS) yr[k] = w[k] * (rowbuf[k] * rs);
+    for (int k = threadIdx.x; k < d; k += ROW_THREADS) {
+      const float o = w[k] * (rowbuf[k] * rs);
+      if (yr) yr[k] = o;
+      if (planes) { rowbuf[k] = o; m = fmaxf(m, fabsf(o)); }
+    }
+  }
+  if (planes) {
+    for (int k = d + threadIdx.x; k < dp; k += ROW_THREADS) rowbuf[k] = 0.f;
+    block_row_split_256(rowbuf, m, dp, planes + r * dp, planes + (rows + r) * dp, inv + r, red);
   }
 }
 
@@ -204,6 +221,87 @@ swiglu_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ g, con
   }
 }
 
+// row forms that also (or only) emit the GEMM operand planes of their results: h feeds down_proj, dg / du feed
+// the backward of gate_proj / up_proj, so the fp32 tensors are optional
+__global__ void __launch_bounds__(ROW_THREADS)
+swiglu_fwd_rows_kernel(const float* __restrict__ g, const float* __restrict__ u, int cols, int cp, float* __restrict__ h,
+                       uint16_t* __restrict__ planes, float* __restrict__ inv, int64_t rows) {
+  extern __shared__ __align__(16) float rowbuf[];   // cp floats
+  __shared__ float red[9];
+  const int64_t r = blockIdx.x;
+  const float* gr = g + r * cols;
+  const float* ur = u + r * cols;
+  float* hr = h ? h + r * cols : nullptr;
+  float m = 0.f;
+  if ((cols & 3) == 0) {
+    for (int k = threadIdx.x * 4; k < cols; k += ROW_THREADS * 4) {
+      const float4 a = ldg_stream(reinterpret_cast<const float4*>(gr + k));
+      const float4 b = ldg_stream(reinterpret_cast<const float4*>(ur + k));
+      float4 o;
+      o.x = a.x * sigmoidf_(a.x) * b.x; o.y = a.y * sigmoidf_(a.y) * b.y;
+      o.z = a.z * sigmoidf_(a.z) * b.z; o.w = a.w * sigmoidf_(a.w) * b.w;
+      if (hr) *reinterpret_cast<float4*>(hr + k) = o;
+      *reinterpret_cast<float4*>(rowbuf + k) = o;
+      m = fmaxf(fmaxf(m, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
+    }
+  } else {
+    for (int k = threadIdx.x; k < cols; k += ROW_THREADS) {
+      const float o = gr[k] * sigmoidf_(gr[k]) * ur[k];
+      if (hr) hr[k] = o;
+      rowbuf[k] = o;
+      m = fmaxf(m, fabsf(o));
+    }
+  }
+  for (int k = cols + threadIdx.x; k < cp; k += ROW_THREADS) rowbuf[k] = 0.f;
+  block_row_split_256(rowbuf, m, cp, planes + r * cp, planes + (rows + r) * cp, inv + r, red);
+}
+
+__global__ void __launch_bounds__(ROW_THREADS)
+swiglu_bwd_rows_kernel(const float* __restrict__ dh, const float* __restrict__ g, const float* __restrict__ u, int cols,
+                       int cp, float* __restrict__ dg, float* __restrict__ du, uint16_t* __restrict__ dg_planes,
+                       float* __restrict__ dg_inv, uint16_t* __restrict__ du_planes, float* __restrict__ du_inv,
+                       int64_t rows) {
+  extern __shared__ __align__(16) float rowbuf[];   // dg [cp] | du [cp]
+  __shared__ float red[9];
+  float* bg = rowbuf;
+  float* bu = rowbuf + cp;
+  const int64_t r = blockIdx.x;
+  const float* dr = dh + r * cols;
+  const float* gr = g + r * cols;
+  const float* ur = u + r * cols;
+  float* dgr = dg ? dg + r * cols : nullptr;
+  float* dur = du ? du + r * cols : nullptr;
+  float mg = 0.f, mu = 0.f;
+  if ((cols & 3) == 0) {
+    for (int k = threadIdx.x * 4; k < cols; k += ROW_THREADS * 4) {
+      const float4 d = ldg_stream(reinterpret_cast<const float4*>(dr + k));
+      const float4 a = *reinterpret_cast<const float4*>(gr + k);       // dg / du may alias g / u: plain loads
+      const float4 b = *reinterpret_cast<const float4*>(ur + k);
+      float4 og, ou;
+      swiglu_bwd_1(d.x, a.x, b.x, og.x, ou.x); swiglu_bwd_1(d.y, a.y, b.y, og.y, ou.y);
+      swiglu_bwd_1(d.z, a.z, b.z, og.z, ou.z); swiglu_bwd_1(d.w, a.w, b.w, og.w, ou.w);
+      if (dgr) *reinterpret_cast<float4*>(dgr + k) = og;
+      if (dur) *reinterpret_cast<float4*>(dur + k) = ou;
+      *reinterpret_cast<float4*>(bg + k) = og;
+      *reinterpret_cast<float4*>(bu + k) = ou;
+      mg = fmaxf(fmaxf(mg, fmaxf(fabsf(og.x), fabsf(og.y))), fmaxf(fabsf(og.z), fabsf(og.w)));
+      mu = fmaxf(fmaxf(mu, fmaxf(fabsf(ou.x), fabsf(ou.y))), fmaxf(fabsf(ou.z), fabsf(ou.w)));
+    }
+  } else {
+    for (int k = threadIdx.x; k < cols; k += ROW_THREADS) {
+      float og, ou;
+      swiglu_bwd_1(dr[k], gr[k], ur[k], og, ou);
+      if (dgr) dgr[k] = og;
+      if (dur) dur[k] = ou;
+      bg[k] = og; bu[k] = ou;
+      mg = fmaxf(mg, fabsf(og)); mu = fmaxf(mu, fabsf(ou));
+    }
+  }
+  for (int k = cols + threadIdx.x; k < cp; k += ROW_THREADS) { bg[k] = 0.f; bu[k] = 0.f; }
+  block_row_split_256(bg, mg, cp, dg_planes + r * cp, dg_planes + (rows + r) * cp, dg_inv + r, red);
+  block_row_split_256(bu, mu, cp, du_planes + r * cp, du_planes + (rows + r) * cp, du_inv + r, red);
+}
+
 // ------------------------------------------------------------------------------ cross entropy
 // One CTA per logits row.  Pass 1 (online max / sum of exponentials) reads the row from HBM, pass 2
 // re-reads it (L2-resident: a row is V*4 bytes and only a few hundred rows are in flight) and
@@ -279,15 +377,20 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 using namespace grasp;
 
 extern "C" int grasp_rmsnorm_fwd(const float* x, const float* w, int64_t rows, int64_t d, float eps, float* y,
-                                 float* rstd, void* stream) {
-  if (!x || !w || !y || !rstd) return bad_arg("rmsnorm_fwd: null");
+                                 float* rstd, void* planes, float* inv, void* stream) {
+  if (!x || !w || !rstd) return bad_arg("rmsnorm_fwd: null");
+  if (!y && !planes) return bad_arg("rmsnorm_fwd: neither y nor planes requested");
+  if (planes && !inv) return bad_arg("rmsnorm_fwd: planes need inv");
   if (rows < 0 || d <= 0 || d > 50 * 1024) return bad_arg("rmsnorm_fwd: rows/d");
-  if (!aligned16(x) || !aligned16(w) || !aligned16(y)) return bad_arg("rmsnorm_fwd: pointers must be 16-byte aligned");
+  if (!aligned16(x) || !aligned16(w) || (y && !aligned16(y))) return bad_arg("rmsnorm_fwd: pointers must be 16-byte aligned");
+  if (planes && (reinterpret_cast<uintptr_t>(planes) & 1023)) return bad_arg("rmsnorm_fwd: planes must be 1024-byte aligned");
   if (rows == 0) return 0;
+  const int64_t dp = round_up(d, 8);
   static size_t granted = 48 * 1024;
-  int rc = row_smem_attr((const void*)rmsnorm_fwd_kernel, (size_t)d * 4, granted, "rmsnorm_fwd attr");
+  int rc = row_smem_attr((const void*)rmsnorm_fwd_kernel, (size_t)dp * 4, granted, "rmsnorm_fwd attr");
   if (rc) return rc;
-  GRASP_LAUNCH(rmsnorm_fwd_kernel, dim3((unsigned)rows), dim3(ROW_THREADS), (size_t)d * 4, stream, x, w, (int)d, eps, y, rstd);
+  GRASP_LAUNCH(rmsnorm_fwd_kernel, dim3((unsigned)rows), dim3(ROW_THREADS), (size_t)dp * 4, stream, x, w, (int)d, (int)dp,
+               eps, y, rstd, static_cast<uint16_t*>(planes), inv, rows);
   GRASP_CHECK_LAST("rmsnorm_fwd_kernel");
   return 0;
 }
@@ -332,25 +435,59 @@ static unsigned elementwise_blocks(int64_t n) {
   return (unsigned)(blocks < 1 ? 1 : blocks);
 }
 
-extern "C" int grasp_swiglu_fwd(const float* g, const float* u, int64_t n, float* h, void* stream) {
-  if (!g || !u || !h) return bad_arg("swiglu_fwd: null");
-  if (n < 0) return bad_arg("swiglu_fwd: n");
-  if (!aligned16(g) || !aligned16(u) || !aligned16(h)) return bad_arg("swiglu_fwd: pointers must be 16-byte aligned");
-  if (n == 0) return 0;
-  GRASP_LAUNCH(swiglu_fwd_kernel, dim3(elementwise_blocks(n)), dim3(256), 0, stream, g, u, n, h);
-  GRASP_CHECK_LAST("swiglu_fwd_kernel");
+extern "C" int grasp_swiglu_fwd(const float* g, const float* u, int64_t rows, int64_t cols, float* h, void* planes,
+                                float* inv, void* stream) {
+  if (!g || !u) return bad_arg("swiglu_fwd: null");
+  if (!h && !planes) return bad_arg("swiglu_fwd: neither h nor planes requested");
+  if (planes && !inv) return bad_arg("swiglu_fwd: planes need inv");
+  if (rows < 0 || cols <= 0) return bad_arg("swiglu_fwd: rows/cols");
+  if (!aligned16(g) || !aligned16(u) || (h && !aligned16(h))) return bad_arg("swiglu_fwd: pointers must be 16-byte aligned");
+  if (rows == 0) return 0;
+  const int64_t n = rows * cols;
+  if (!planes) {
+    GRASP_LAUNCH(swiglu_fwd_kernel, dim3(elementwise_blocks(n)), dim3(256), 0, stream, g, u, n, h);
+    GRASP_CHECK_LAST("swiglu_fwd_kernel");
+    return 0;
+  }
+  if (reinterpret_cast<uintptr_t>(planes) & 1023) return bad_arg("swiglu_fwd: planes must be 1024-byte aligned");
+  const int64_t cp = round_up(cols, 8);
+  if (cp * 4 > 200 * 1024) return bad_arg("swiglu_fwd: row too long for the fused operand form");
+  static size_t granted = 48 * 1024;
+  int rc = row_smem_attr((const void*)swiglu_fwd_rows_kernel, (size_t)cp * 4, granted, "swiglu_fwd attr");
+  if (rc) return rc;
+  GRASP_LAUNCH(swiglu_fwd_rows_kernel, dim3((unsigned)rows), dim3(ROW_THREADS), (size_t)cp * 4, stream, g, u, (int)cols,
+               (int)cp, h, static_cast<uint16_t*>(planes), inv, rows);
+  GRASP_CHECK_LAST("swiglu_fwd_rows_kernel");
   return 0;
 }
 
-extern "C" int grasp_swiglu_bwd(const float* dh, const float* g, const float* u, int64_t n, float* dg, float* du,
-                                void* stream) {
-  if (!dh || !g || !u || !dg || !du) return bad_arg("swiglu_bwd: null");
-  if (n < 0) return bad_arg("swiglu_bwd: n");
-  if (!aligned16(dh) || !aligned16(g) || !aligned16(u) || !aligned16(dg) || !aligned16(du))
+extern "C" int grasp_swiglu_bwd(const float* dh, const float* g, const float* u, int64_t rows, int64_t cols, float* dg,
+                                float* du, void* dg_planes, float* dg_inv, void* du_planes, float* du_inv, void* stream) {
+  if (!dh || !g || !u) return bad_arg("swiglu_bwd: null");
+  const bool want_planes = dg_planes || du_planes;
+  if (want_planes && !(dg_planes && du_planes && dg_inv && du_inv)) return bad_arg("swiglu_bwd: both operand forms or none");
+  if (!want_planes && !(dg && du)) return bad_arg("swiglu_bwd: nothing requested");
+  if ((dg == nullptr) != (du == nullptr)) return bad_arg("swiglu_bwd: dg and du come together");
+  if (rows < 0 || cols <= 0) return bad_arg("swiglu_bwd: rows/cols");
+  if (!aligned16(dh) || !aligned16(g) || !aligned16(u) || (dg && (!aligned16(dg) || !aligned16(du))))
     return bad_arg("swiglu_bwd: pointers must be 16-byte aligned");
-  if (n == 0) return 0;
-  GRASP_LAUNCH(swiglu_bwd_kernel, dim3(elementwise_blocks(n)), dim3(256), 0, stream, dh, g, u, n, dg, du);
-  GRASP_CHECK_LAST("swiglu_bwd_kernel");
+  if (rows == 0) return 0;
+  const int64_t n = rows * cols;
+  if (!want_planes) {
+    GRASP_LAUNCH(swiglu_bwd_kernel, dim3(elementwise_blocks(n)), dim3(256), 0, stream, dh, g, u, n, dg, du);
+    GRASP_CHECK_LAST("swiglu_bwd_kernel");
+    return 0;
+  }
+  if ((reinterpret_cast<uintptr_t>(dg_planes) & 1023) || (reinterpret_cast<uintptr_t>(du_planes) & 1023))
+    return bad_arg("swiglu_bwd: planes must be 1024-byte aligned");
+  const int64_t cp = round_up(cols, 8);
+  if (cp * 8 > 200 * 1024) return bad_arg("swiglu_bwd: row too long for the fused operand form");
+  static size_t granted = 48 * 1024;
+  int rc = row_smem_attr((const void*)swiglu_bwd_rows_kernel, (size_t)cp * 8, granted, "swiglu_bwd attr");
+  if (rc) return rc;
+  GRASP_LAUNCH(swiglu_bwd_rows_kernel, dim3((unsigned)rows), dim3(ROW_THREADS), (size_t)cp * 8, stream, dh, g, u, (int)cols,
+               (int)cp, dg, du, static_cast<uint16_t*>(dg_planes), dg_inv, static_cast<uint16_t*>(du_planes), du_inv, rows);
+  GRASP_CHECK_LAST("swiglu_bwd_rows_kernel");
   return 0;
 }
 

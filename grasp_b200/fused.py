@@ -89,6 +89,25 @@ class CudaBackend:
             return ops.gemm(dy, x, ta=True)
         return ops.gemm(dy, x, ta=True, beta=1.0, C_out=G)
 
+    # -- row kernels that hand their result over as a prepared operand (the fp32 tensor only on request)
+    @staticmethod
+    def rmsnorm_fwd_op(x, w, eps, keep_y):
+        return ops.rmsnorm_fwd(x, w, eps, want_y=keep_y, want_operand=True)
+
+    @staticmethod
+    def swiglu_fwd_op(g, u, keep_h):
+        if g.shape[1] > 51200:                              # row does not fit in shared memory: two kernels
+            h = ops.swiglu_fwd(g, u)
+            return h, ops.split_f16(h, _lib.SCALE_ROWS)
+        return ops.swiglu_fwd(g, u, want_h=keep_h, want_operand=True)
+
+    @staticmethod
+    def swiglu_bwd_op(dh, g, u, keep_grads):
+        if g.shape[1] > 25600:
+            dg, du = ops.swiglu_bwd(dh, g, u, inplace=True)
+            return dg, du, ops.split_f16(dg, _lib.SCALE_ROWS), ops.split_f16(du, _lib.SCALE_ROWS)
+        return ops.swiglu_bwd(dh, g, u, inplace=True, want_grads=keep_grads, want_operands=True)
+
     # -- row kernels
     rmsnorm_fwd = staticmethod(ops.rmsnorm_fwd)
     rmsnorm_bwd = staticmethod(ops.rmsnorm_bwd)
@@ -225,8 +244,13 @@ class FusedLlama:
         L = self.r.layers[i]
         att, mlp = L.self_attn, L.mlp
         D = att.head_dim
-        xn, rstd1 = be.rmsnorm_fwd(x, L.input_layernorm.weight, L.input_layernorm.variance_epsilon)
-        xo = be.prep(xn)
+        g_attn_in = any(self._is_grasp(m) for m in (att.q_proj, att.k_proj, att.v_proj))
+        g_mlp_in = any(self._is_grasp(m) for m in (mlp.gate_proj, mlp.up_proj))
+        g_down = self._is_grasp(mlp.down_proj)
+        # the norms and the gated activation feed linears only: they hand over the operand form directly and
+        # write the fp32 tensor only where a GRASPLayer needs it for G += dY^T X
+        xn, rstd1, xo = be.rmsnorm_fwd_op(x, L.input_layernorm.weight, L.input_layernorm.variance_epsilon,
+                                          keep and g_attn_in)
         q = self.lin_fwd(att.q_proj, xo, tag=i)
         k = self.lin_fwd(att.k_proj, xo, tag=i)
         v = self.lin_fwd(att.v_proj, xo, tag=i)
@@ -237,21 +261,20 @@ class FusedLlama:
         a, actx = sdpa_fwd(q, k, v, B, S, H, Hkv, D, att.scaling, keep)
         x2 = self.lin_fwd(att.o_proj, be.prep(a), tag=i)
         x2 += x
-        xn2, rstd2 = be.rmsnorm_fwd(x2, L.post_attention_layernorm.weight, L.post_attention_layernorm.variance_epsilon)
-        xo2 = be.prep(xn2)
+        xn2, rstd2, xo2 = be.rmsnorm_fwd_op(x2, L.post_attention_layernorm.weight,
+                                            L.post_attention_layernorm.variance_epsilon, keep and g_mlp_in)
         g = self.lin_fwd(mlp.gate_proj, xo2, tag=i)
         u = self.lin_fwd(mlp.up_proj, xo2, tag=i)
         del xo2
-        h = be.swiglu_fwd(g, u)
-        x3 = self.lin_fwd(mlp.down_proj, be.prep(h), tag=i)
+        h, ho = be.swiglu_fwd_op(g, u, keep and g_down)
+        x3 = self.lin_fwd(mlp.down_proj, ho, tag=i)
+        del ho
         x3 += x2
         if not keep:
             return x3, None
-        g_attn_in = any(self._is_grasp(m) for m in (att.q_proj, att.k_proj, att.v_proj))
-        g_mlp_in = any(self._is_grasp(m) for m in (mlp.gate_proj, mlp.up_proj))
         saved = {"x": x, "rstd1": rstd1, "xn": xn if g_attn_in else None, "actx": actx, "H": H, "Hkv": Hkv,
                  "a": a if self._is_grasp(att.o_proj) else None, "x2": x2, "rstd2": rstd2,
-                 "xn2": xn2 if g_mlp_in else None, "g": g, "u": u, "h": h if self._is_grasp(mlp.down_proj) else None}
+                 "xn2": xn2 if g_mlp_in else None, "g": g, "u": u, "h": h if g_down else None}
         return x3, saved
 
     def layer_bwd(self, i, sv, dx3, B, S, cos, sin, need_dx: bool):
@@ -271,15 +294,19 @@ class FusedLlama:
         dx2 = None
         if need_x2 or gg or gu:
             dh = self.lin_bwd(mlp.down_proj, be.prep(dx3), tag=i)
-            dg, du = be.swiglu_bwd(dh, sv["g"], sv["u"])
+            if need_x2:          # dg / du go on into the gate / up backward: operand form straight from the kernel
+                dg, du, dgo, duo = be.swiglu_bwd_op(dh, sv["g"], sv["u"], gg or gu)
+            else:
+                dg, du = be.swiglu_bwd(dh, sv["g"], sv["u"])
             del dh
             if gg:
                 self.harvest(mlp.gate_proj, dg, sv["xn2"])
             if gu:
                 self.harvest(mlp.up_proj, du, sv["xn2"])
             if need_x2:
-                dxn2 = self.lin_bwd(mlp.gate_proj, be.prep(dg), tag=i)
-                self.lin_bwd(mlp.up_proj, be.prep(du), out=dxn2, beta=1.0, tag=i)
+                dxn2 = self.lin_bwd(mlp.gate_proj, dgo, tag=i)
+                self.lin_bwd(mlp.up_proj, duo, out=dxn2, beta=1.0, tag=i)
+                del dgo, duo
                 dx2 = be.rmsnorm_bwd(dxn2, sv["x2"], L.post_attention_layernorm.weight, sv["rstd2"], add=dx3)
         if not need_x2:
             return None
@@ -316,9 +343,10 @@ class FusedLlama:
         be, r = self.be, self.r
         d = x.shape[1]
         xs = x.view(B, S, d)[:, :-1].reshape(B * (S - 1), d)          # the last position has no target
-        xn, rstd = be.rmsnorm_fwd(xs, r.norm.weight, r.norm.variance_epsilon)
+        _, rstd, xno = be.rmsnorm_fwd_op(xs, r.norm.weight, r.norm.variance_epsilon, False)
         wo = be.wprep(r.head.weight, "head")
-        logits = be.mm_nt(be.prep(xn), wo)
+        logits = be.mm_nt(xno, wo)
+        del xno
         if r.head.bias is not None:
             logits += r.head.bias
         lab = labels[:, 1:]

@@ -397,6 +397,18 @@ class Operand:
         return self._base.numel() + self.inv.numel() * 4
 
 
+def _new_operand(rows: int, cols: int, mode: int, dev) -> Operand:
+    lib = _lib.load()
+    nbytes = lib.grasp_gemm_planes_bytes(rows, cols)
+    base = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+    op = Operand()
+    op._base = base
+    op.planes = base.data_ptr() + (-base.data_ptr()) % 1024
+    op.inv = torch.empty(rows if mode == _lib.SCALE_ROWS else max(rows, cols) + 1, dtype=torch.float32, device=dev)
+    op.rows, op.cols, op.mode, op.src, op.version = rows, cols, mode, None, 0
+    return op
+
+
 def split_f16(x: torch.Tensor, mode: int = _lib.SCALE_ROWS, keep_src: bool = False) -> Operand:
     """Planes of a contiguous fp32 [rows, cols] matrix; SCALE_ROWS for activations, SCALE_TENSOR for weights."""
     lib = _lib.load()
@@ -407,15 +419,7 @@ def split_f16(x: torch.Tensor, mode: int = _lib.SCALE_ROWS, keep_src: bool = Fal
     rows, cols = x.shape
     if rows == 0 or cols == 0:
         raise ValueError("split_f16: empty matrix")
-    nbytes = lib.grasp_gemm_planes_bytes(rows, cols)
-    base = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
-    off = (-base.data_ptr()) % 1024
-    op = Operand()
-    op._base = base
-    op.planes = base.data_ptr() + off
-    n_inv = rows if mode == _lib.SCALE_ROWS else max(rows, cols) + 1
-    op.inv = torch.empty(n_inv, dtype=torch.float32, device=dev)
-    op.rows, op.cols, op.mode = rows, cols, mode
+    op = _new_operand(rows, cols, mode, dev)
     op.src = x if keep_src else None
     op.version = x._version
     with torch.cuda.device(dev):
@@ -463,19 +467,24 @@ def _rows2d(t: torch.Tensor, name: str) -> torch.Tensor:
     return _f32c(t, name)
 
 
-def rmsnorm_fwd(x: torch.Tensor, w: torch.Tensor, eps: float) -> Tuple[torch.Tensor, torch.Tensor]:
+def rmsnorm_fwd(x: torch.Tensor, w: torch.Tensor, eps: float, want_y: bool = True, want_operand: bool = False):
+    """(y, rstd) -- or (y or None, rstd, Operand) with want_operand: y as a prepared GEMM operand straight from the kernel."""
     lib = _lib.load()
     dev = _need_cuda(x, w)
     x, w = _rows2d(x, "x"), _f32c(w, "w")
     rows, d = x.shape
-    y = torch.empty_like(x)
+    if not (want_y or want_operand):
+        raise ValueError("rmsnorm_fwd: nothing requested")
+    y = torch.empty_like(x) if want_y else None
     rstd = torch.empty(rows, dtype=torch.float32, device=dev)
+    op = _new_operand(rows, d, _lib.SCALE_ROWS, dev) if (want_operand and rows > 0) else None
     with torch.cuda.device(dev):
         t0 = timers.start()
-        check(lib.grasp_rmsnorm_fwd(x.data_ptr(), w.data_ptr(), rows, d, float(eps), y.data_ptr(), rstd.data_ptr(),
-                                    _stream()), "grasp_rmsnorm_fwd")
-        timers.stop("grasp_rowops", t0, bytes_=8.0 * rows * d)
-    return y, rstd
+        check(lib.grasp_rmsnorm_fwd(x.data_ptr(), w.data_ptr(), rows, d, float(eps), y.data_ptr() if y is not None else None,
+                                    rstd.data_ptr(), op.planes if op is not None else None,
+                                    op.inv.data_ptr() if op is not None else None, _stream()), "grasp_rmsnorm_fwd")
+        timers.stop("grasp_rowops", t0, bytes_=4.0 * rows * d * (1 + int(want_y) + int(op is not None)))
+    return (y, rstd, op) if want_operand else (y, rstd)
 
 
 def rmsnorm_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, rstd: torch.Tensor,
@@ -519,37 +528,54 @@ def rope_(x: torch.Tensor, seq: int, heads: int, hd: int, cos: torch.Tensor, sin
     return x
 
 
-def swiglu_fwd(g: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
+def swiglu_fwd(g: torch.Tensor, u: torch.Tensor, want_h: bool = True, want_operand: bool = False):
+    """h = silu(g) * u -- or (h or None, Operand of h) with want_operand."""
     lib = _lib.load()
     dev = _need_cuda(g, u)
-    g, u = _f32c(g, "g"), _f32c(u, "u")
+    g, u = _rows2d(g, "g"), _rows2d(u, "u")
     if g.shape != u.shape:
         raise ValueError("swiglu: shapes differ")
-    h = torch.empty_like(g)
+    rows, cols = g.shape
+    if not (want_h or want_operand):
+        raise ValueError("swiglu_fwd: nothing requested")
+    h = torch.empty_like(g) if want_h else None
+    op = _new_operand(rows, cols, _lib.SCALE_ROWS, dev) if (want_operand and rows > 0) else None
     with torch.cuda.device(dev):
         t0 = timers.start()
-        check(lib.grasp_swiglu_fwd(g.data_ptr(), u.data_ptr(), g.numel(), h.data_ptr(), _stream()), "grasp_swiglu_fwd")
-        timers.stop("grasp_rowops", t0, bytes_=12.0 * g.numel())
-    return h
+        check(lib.grasp_swiglu_fwd(g.data_ptr(), u.data_ptr(), rows, cols, h.data_ptr() if h is not None else None,
+                                   op.planes if op is not None else None, op.inv.data_ptr() if op is not None else None,
+                                   _stream()), "grasp_swiglu_fwd")
+        timers.stop("grasp_rowops", t0, bytes_=4.0 * g.numel() * (2 + int(want_h) + int(op is not None)))
+    return (h, op) if want_operand else h
 
 
-def swiglu_bwd(dh: torch.Tensor, g: torch.Tensor, u: torch.Tensor, inplace: bool = False):
-    """(dg, du); inplace=True overwrites g and u with their gradients."""
+def swiglu_bwd(dh: torch.Tensor, g: torch.Tensor, u: torch.Tensor, inplace: bool = False, want_grads: bool = True,
+               want_operands: bool = False):
+    """(dg, du); inplace=True overwrites g and u with their gradients.  With want_operands the result is
+    (dg or None, du or None, Operand of dg, Operand of du): the gradients as prepared GEMM operands."""
     lib = _lib.load()
     dev = _need_cuda(dh, g, u)
-    dh = _f32c(dh, "dh")
+    dh = _rows2d(dh, "dh")
     if g.dtype != torch.float32 or u.dtype != torch.float32 or not g.is_contiguous() or not u.is_contiguous():
         raise TypeError("swiglu_bwd: g and u must be contiguous float32")
-    if g.shape != u.shape or dh.shape != g.shape:
+    if g.dim() != 2 or g.shape != u.shape or dh.shape != g.shape:
         raise ValueError("swiglu: shapes differ")
-    dg = g if inplace else torch.empty_like(g)
-    du = u if inplace else torch.empty_like(u)
+    if not (want_grads or want_operands):
+        raise ValueError("swiglu_bwd: nothing requested")
+    rows, cols = g.shape
+    dg = (g if inplace else torch.empty_like(g)) if want_grads else None
+    du = (u if inplace else torch.empty_like(u)) if want_grads else None
+    og = _new_operand(rows, cols, _lib.SCALE_ROWS, dev) if (want_operands and rows > 0) else None
+    ou = _new_operand(rows, cols, _lib.SCALE_ROWS, dev) if (want_operands and rows > 0) else None
     with torch.cuda.device(dev):
         t0 = timers.start()
-        check(lib.grasp_swiglu_bwd(dh.data_ptr(), g.data_ptr(), u.data_ptr(), g.numel(), dg.data_ptr(), du.data_ptr(),
+        check(lib.grasp_swiglu_bwd(dh.data_ptr(), g.data_ptr(), u.data_ptr(), rows, cols,
+                                   dg.data_ptr() if dg is not None else None, du.data_ptr() if du is not None else None,
+                                   og.planes if og is not None else None, og.inv.data_ptr() if og is not None else None,
+                                   ou.planes if ou is not None else None, ou.inv.data_ptr() if ou is not None else None,
                                    _stream()), "grasp_swiglu_bwd")
-        timers.stop("grasp_rowops", t0, bytes_=20.0 * g.numel())
-    return dg, du
+        timers.stop("grasp_rowops", t0, bytes_=4.0 * g.numel() * (3 + 2 * int(want_grads) + 2 * int(og is not None)))
+    return (dg, du, og, ou) if want_operands else (dg, du)
 
 
 def ce_loss_bwd_(logits: torch.Tensor, labels: torch.Tensor, coef: torch.Tensor) -> torch.Tensor:

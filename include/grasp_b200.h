@@ -198,15 +198,22 @@ int    grasp_gemm_f16x3_planes(int64_t M, int64_t N, int64_t K, float alpha,
  *             logits overwritten by dloss/dlogits = coef[t] * (softmax - onehot);
  *             label < 0 -> loss 0, gradient 0 (ignore_index)
  * ------------------------------------------------------------------------- */
+/* y and/or the GEMM operand form of y (planes + inv as written by grasp_gemm_split_f16 with
+ * GRASP_SCALE_ROWS) -- the consumer of a norm is always a linear; either may be NULL, not both */
 int grasp_rmsnorm_fwd(const float* x, const float* w, int64_t rows, int64_t d, float eps,
-                      float* y, float* rstd, void* stream);
+                      float* y, float* rstd, void* planes, float* inv, void* stream);
 int grasp_rmsnorm_bwd(const float* dy, const float* x, const float* w, const float* rstd,
                       const float* add, int64_t rows, int64_t d, float* dx, void* stream);
 int grasp_rope_inplace(float* x, int64_t tokens, int64_t seq, int64_t heads, int64_t hd,
                        const float* cos, const float* sin, int64_t cs_batch, int inverse, void* stream);
-int grasp_swiglu_fwd(const float* g, const float* u, int64_t n, float* h, void* stream);
-int grasp_swiglu_bwd(const float* dh, const float* g, const float* u, int64_t n,
-                     float* dg, float* du, void* stream);
+/* g, u, h, dh, dg, du are [rows][cols] contiguous.  h / (dg, du) may be NULL when only their operand
+ * forms are wanted (h feeds down_proj, dg / du the backward of gate_proj / up_proj); the operand forms
+ * need cols <= 51200 (forward) / 25600 (backward).  dg / du may alias g / u. */
+int grasp_swiglu_fwd(const float* g, const float* u, int64_t rows, int64_t cols, float* h,
+                     void* planes, float* inv, void* stream);
+int grasp_swiglu_bwd(const float* dh, const float* g, const float* u, int64_t rows, int64_t cols,
+                     float* dg, float* du, void* dg_planes, float* dg_inv,
+                     void* du_planes, float* du_inv, void* stream);
 int grasp_ce_loss_bwd(float* logits, const int64_t* labels, const float* coef, int64_t rows, int64_t V,
                       float* loss, void* stream);
 

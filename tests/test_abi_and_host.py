@@ -41,11 +41,11 @@ def test_bad_arguments_are_rejected_before_any_launch():
     assert lib.grasp_gemm_f32(0, 0, 4, 4, 4, 1.0, None, 4, None, 4, 0.0, None, 4, 0, None, 0, None) < 0
     assert lib.grasp_gemm_split_f16(None, 8, 4, 8, 0, None, None, None) < 0
     assert lib.grasp_gemm_f16x3_planes(4, 4, 4, 1.0, None, None, None, 0, None, 0.0, None, 4, None) < 0
-    assert lib.grasp_rmsnorm_fwd(None, None, 4, 8, 1e-5, None, None, None) < 0
+    assert lib.grasp_rmsnorm_fwd(None, None, 4, 8, 1e-5, None, None, None, None, None) < 0
     assert lib.grasp_rmsnorm_bwd(None, None, None, None, None, 4, 8, None, None) < 0
     assert lib.grasp_rope_inplace(None, 4, 4, 1, 8, None, None, 0, 0, None) < 0
-    assert lib.grasp_swiglu_fwd(None, None, 4, None, None) < 0
-    assert lib.grasp_swiglu_bwd(None, None, None, 4, None, None, None) < 0
+    assert lib.grasp_swiglu_fwd(None, None, 4, 8, None, None, None, None) < 0
+    assert lib.grasp_swiglu_bwd(None, None, None, 4, 8, None, None, None, None, None, None, None) < 0
     assert lib.grasp_ce_loss_bwd(None, None, None, 4, 8, None, None) < 0
     assert lib.grasp_gemm_planes_bytes(8176, 4096) == 2 * 8176 * 4096 * 2      # two fp16 planes, already 1 KiB-aligned
     assert lib.grasp_gemm_planes_bytes(3, 5) == 1024                            # cols padded to 8, size to 1 KiB

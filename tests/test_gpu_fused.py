@@ -235,3 +235,47 @@ def test_perplexity_evaluator_on_the_fused_route(cuda):
     got_c = evaluate.evaluate_perplexity(gm, tok, None, cuda)
     ref_c = restate.perplexity(copy.deepcopy(gm.model).to("cpu"), tok)
     assert abs(got_c - ref_c) / ref_c < 1e-4
+
+
+@pytest.mark.parametrize("rows,d,f", [(37, 4096, 11008), (5, 1000, 2744), (3, 66, 177)])
+def test_row_kernels_emit_gemm_operands(cuda, rows, d, f):
+    """RMSNorm / SwiGLU forward / SwiGLU backward hand their results over as prepared GEMM operands (planes +
+    row scales) with or without the fp32 tensor: the product of that operand with a weight must equal the
+    product of the separately split fp32 result, bit for bit, and the fp32 outputs must not change."""
+    from grasp_b200 import _lib, ops
+    g = torch.Generator().manual_seed(rows + d)
+    x = torch.randn(rows, d, generator=g).to(cuda)
+    w = (1 + 0.1 * torch.randn(d, generator=g)).to(cuda)
+    W = (torch.randn(24, d, generator=g) * 0.05).to(cuda)
+    Wo = ops.split_f16(W, _lib.SCALE_TENSOR)
+    y, rstd = ops.rmsnorm_fwd(x, w, 1e-5)
+    y2, rstd2, op = ops.rmsnorm_fwd(x, w, 1e-5, want_y=True, want_operand=True)
+    none, rstd3, op3 = ops.rmsnorm_fwd(x, w, 1e-5, want_y=False, want_operand=True)
+    assert none is None and torch.equal(y, y2) and torch.equal(rstd, rstd2) and torch.equal(rstd, rstd3)
+    ref = ops.gemm_planes(ops.split_f16(y), Wo)
+    assert torch.equal(ops.gemm_planes(op, Wo), ref) and torch.equal(ops.gemm_planes(op3, Wo), ref)
+
+    a = (torch.randn(rows, f, generator=g) * 3).to(cuda)
+    b = torch.randn(rows, f, generator=g).to(cuda)
+    dh = torch.randn(rows, f, generator=g).to(cuda)
+    Wf = (torch.randn(16, f, generator=g) * 0.05).to(cuda)
+    Wfo = ops.split_f16(Wf, _lib.SCALE_TENSOR)
+    h = ops.swiglu_fwd(a, b)
+    h2, hop = ops.swiglu_fwd(a, b, want_h=True, want_operand=True)
+    h3, hop3 = ops.swiglu_fwd(a, b, want_h=False, want_operand=True)
+    assert h3 is None and torch.equal(h, h2)
+    ref = ops.gemm_planes(ops.split_f16(h), Wfo)
+    assert torch.equal(ops.gemm_planes(hop, Wfo), ref) and torch.equal(ops.gemm_planes(hop3, Wfo), ref)
+
+    dg, du = ops.swiglu_bwd(dh, a, b)
+    dg2, du2, gop, uop = ops.swiglu_bwd(dh, a, b, want_grads=True, want_operands=True)
+    n1, n2, gop3, uop3 = ops.swiglu_bwd(dh, a, b, want_grads=False, want_operands=True)
+    assert n1 is None and n2 is None and torch.equal(dg, dg2) and torch.equal(du, du2)
+    for o, o3, t in ((gop, gop3, dg), (uop, uop3, du)):
+        ref = ops.gemm_planes(ops.split_f16(t), Wfo)
+        assert torch.equal(ops.gemm_planes(o, Wfo), ref) and torch.equal(ops.gemm_planes(o3, Wfo), ref)
+    # in place: g and u are overwritten by their gradients while the operands are produced
+    a2, b2 = a.clone(), b.clone()
+    dg4, du4, gop4, _ = ops.swiglu_bwd(dh, a2, b2, inplace=True, want_operands=True)
+    assert dg4.data_ptr() == a2.data_ptr() and torch.equal(dg4, dg) and torch.equal(du4, du)
+    assert torch.equal(ops.gemm_planes(gop4, Wfo), ops.gemm_planes(gop, Wfo))

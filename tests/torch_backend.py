@@ -42,6 +42,18 @@ class TorchBackend:
         rstd = torch.rsqrt(x.pow(2).mean(-1) + eps)
         return self._rms(x, w, eps), rstd
 
+    def rmsnorm_fwd_op(self, x, w, eps, keep_y):
+        y, rstd = self.rmsnorm_fwd(x, w, eps)
+        return (y if keep_y else None), rstd, y
+
+    def swiglu_fwd_op(self, g, u, keep_h):
+        h = self.swiglu_fwd(g, u)
+        return (h if keep_h else None), h
+
+    def swiglu_bwd_op(self, dh, g, u, keep_grads):
+        dg, du = self.swiglu_bwd(dh, g, u)
+        return (dg if keep_grads else None), (du if keep_grads else None), dg, du
+
     def rmsnorm_bwd(self, dy, x, w, rstd, add=None):
         xl = x.detach().requires_grad_(True)
         with torch.enable_grad():
