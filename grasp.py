@@ -69,20 +69,32 @@ def compress(grasp_model: GRASPModel, calibration_dataloader: DataLoader, layers
     if threshold_ratio is not None:
         logger.info("=======> Adaptive rank selection by taylor threshold %s", threshold_ratio)
 
-    if hoist_svd and not allocation_aware:
-        # the SVDs factor ORIGINAL weights, so all of them can run up front in batched launches
+    def target_names(layer_id):
         names = []
-        for layer_id in layers_id:
-            if mlp_target_layer_types is not None:
-                names += grasp_model.block_target_names(layer_id, "mlp", mlp_target_layer_types)
-            if attn_target_layer_types is not None:
-                names += grasp_model.block_target_names(layer_id, "attention", attn_target_layer_types)
-        grasp_model.precompute_svd(names, device=device)
-    # one forward sweep caches the input of every selected layer for all calibration samples
+        if mlp_target_layer_types is not None:
+            names += grasp_model.block_target_names(layer_id, "mlp", mlp_target_layer_types)
+        if attn_target_layer_types is not None:
+            names += grasp_model.block_target_names(layer_id, "attention", attn_target_layer_types)
+        return names
+
+    def hoist(position):
+        # the SVDs factor ORIGINAL weights, so those of the next layers can run ahead in batched launches;
+        # how many layers at once is bounded by the memory their factors take (all of them at configs[1])
+        if not (hoist_svd and not allocation_aware):
+            return
+        ahead = layers_id[position:]
+        if not ahead or all(n in grasp_model._svd_cache for n in target_names(ahead[0])):
+            return
+        count = grasp_model.svd_hoist_layers(ahead, target_names, device=device)
+        grasp_model.precompute_svd([n for l in ahead[:count] for n in target_names(l)], device=device)
+
+    hoist(0)
+    # one forward sweep caches the input of the selected layers for all calibration samples (as many as fit)
     grasp_model.prepare_calibration(calibration_dataloader, layers_id, device=device)
 
     blocks = (("mlp", mlp_target_layer_types), ("attention", attn_target_layer_types))
-    for layer_id in tqdm(layers_id, desc="GRASP Compressing", total=len(layers_id), leave=True):
+    for position, layer_id in enumerate(tqdm(layers_id, desc="GRASP Compressing", total=len(layers_id), leave=True)):
+        hoist(position)
         for block_type, target_layer_types in blocks:
             skip_flag = grasp_model.compress_block(layer_id=layer_id, block_type=block_type,
                                                    target_layer_types=target_layer_types, verbose=verbose,

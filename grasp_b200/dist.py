@@ -69,6 +69,16 @@ def all_reduce_sum_(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+def all_min_int(value: int, device) -> int:
+    """The smallest `value` over the ranks (plans that decide how many collectives follow must agree)."""
+    if not (initialized() and td.get_world_size() > 1):
+        return int(value)
+    dev = torch.device(device)
+    t = torch.tensor([int(value)], dtype=torch.int64, device=dev if dev.type == "cuda" else "cpu")
+    td.all_reduce(t, op=td.ReduceOp.MIN)
+    return int(t.item())
+
+
 def all_reduce_sum_many_(tensors: Sequence[torch.Tensor]) -> None:
     """One collective for a list of same-dtype vectors (the sigma-gradients of a block: 48-64 KB)."""
     if not (initialized() and td.get_world_size() > 1) or not tensors:

@@ -13,6 +13,7 @@ them to autograd / per-call library dispatch:
 from __future__ import annotations
 
 import contextlib
+import logging
 import os
 from collections import OrderedDict
 from typing import Iterable, List, Sequence
@@ -20,6 +21,8 @@ from typing import Iterable, List, Sequence
 import torch
 
 from . import dist, ops
+
+logger = logging.getLogger(__name__)
 
 # "torch": the three linear GEMMs of a GRASPLayer go through torch.matmul (cuBLAS fp32);
 # "grasp": they go through grasp_gemm_f32 (split-bf16 tcgen05 path of this library).
@@ -92,16 +95,36 @@ def batched_svd(weights: Sequence[torch.Tensor], max_group: int = 8):
     return _batched_svd_local(weights, max_group)
 
 
+class SvdNotConverged(RuntimeError):
+    pass
+
+
 def _batched_svd_local(weights: Sequence[torch.Tensor], max_group: int = 8):
     groups: "OrderedDict[tuple, list]" = OrderedDict()
     for i, w in enumerate(weights):
         groups.setdefault(tuple(w.shape), []).append(i)
     out = [None] * len(weights)
+    infos = []
     for idxs in groups.values():
         for s in range(0, len(idxs), max_group):
             chunk = idxs[s:s + max_group]
-            for i, usv in zip(chunk, ops.svd_batched([weights[i] for i in chunk])):
+            usvs, info = ops.svd_batched([weights[i] for i in chunk], return_info=True)
+            infos.append((chunk, info))
+            for i, usv in zip(chunk, usvs):
                 out[i] = usv
+    # one synchronisation for the whole call: a Jacobi run that hit its sweep limit would hand non-orthogonal
+    # factors to scoring and compile, so it is retried with the pure-fp32 path and refused if that fails too
+    flags = torch.cat([info[:, 1] for _, info in infos]).cpu().tolist() if infos else []
+    order = [i for chunk, _ in infos for i in chunk]
+    for i, ok in zip(order, flags):
+        if ok:
+            continue
+        logger.warning("SVD of matrix %d %s did not converge; retrying on the fp32 CUDA-core path", i,
+                       tuple(weights[i].shape))
+        usvs, info = ops.svd_batched([weights[i]], prec=ops.PREC_SIMT, max_sweeps=48, return_info=True)
+        if not int(info[0, 1].item()):
+            raise SvdNotConverged(f"SVD of a {tuple(weights[i].shape)} matrix did not converge")
+        out[i] = usvs[0]
     return out
 
 
@@ -290,16 +313,34 @@ class LlamaRunner:
                                                                       hf_model.lm_head)
         self.micro_batch = micro_batch
         self.use_grasp_gemm = use_grasp_gemm
-        self.cache = {}          # layer id -> [n_samples, S, d] input of that layer
-        self.cache_key = None    # id of the CalibrationSet the cache belongs to
-        self.ckpt = {}           # activation checkpoints written by the scoring pass
-        self.ckpt_key = None
+        # activation store: layer id -> [n_samples, S, d] input of that layer, valid while every layer below
+        # is an untouched original (entries of the scoring pass are checkpoints, the others prefix caches)
+        self.cache = {}
+        self.cache_key = None    # id of the CalibrationSet the store belongs to
+        self.store_key = None    # ... and of the one its byte budget was planned for
+        self.store_budget = None
+        self.store_per = 0
+        gb = os.environ.get("GRASP_B200_MEM_BUDGET_GB")
+        self.budget_bytes = int(float(gb) * 2**30) if gb else None
+        mb = os.environ.get("GRASP_B200_STORE_MB")         # fixed size of the activation store (else planned)
+        self.store_cap_bytes = int(float(mb) * 2**20) if mb else None
+
+    # model families whose forward IS embed -> decoder layers (causal, no mask) -> norm -> head, verified
+    # against transformers' own forward in tests/test_engine_cpu.py; anything else (embedding normalisers,
+    # logit soft-capping, sliding-window / per-layer masks) takes the generic whole-model path
+    SUPPORTED_MODEL_TYPES = ("llama",)
 
     @staticmethod
     def supports(hf_model) -> bool:
         m = getattr(hf_model, "model", None)
         ok = all(hasattr(m, a) for a in ("embed_tokens", "layers", "norm", "rotary_emb")) and hasattr(hf_model, "lm_head")
-        impl = getattr(getattr(hf_model, "config", None), "_attn_implementation", "sdpa")
+        cfg = getattr(hf_model, "config", None)
+        impl = getattr(cfg, "_attn_implementation", "sdpa")
+        if getattr(cfg, "model_type", None) not in LlamaRunner.SUPPORTED_MODEL_TYPES:
+            return False
+        if getattr(cfg, "sliding_window", None) or getattr(cfg, "layer_types", None) and \
+                any(t != "full_attention" for t in cfg.layer_types):
+            return False
         return bool(ok and impl in ("sdpa", None))
 
     @property
@@ -356,63 +397,155 @@ class LlamaRunner:
         # only positions [0, S-1) enter the loss: drop the last one before the head instead of slicing the logits
         logits = self.head(self.norm(hidden[:, :-1]))
         B, S1, V = logits.shape
-        per_tok = F.cross_entropy(logits.reshape(-1, V).float(), labels[:, 1:].reshape(-1), reduction="none")
-        return (per_tok.view(B, S1).mean(dim=1) * weights).sum()
+        lab = labels[:, 1:]
+        per_tok = F.cross_entropy(logits.reshape(-1, V).float(), lab.reshape(-1), reduction="none", ignore_index=-100)
+        valid = (lab != -100).sum(dim=1).clamp(min=1)          # HF averages over the non-ignored labels
+        return (per_tok.view(B, S1).sum(dim=1) / valid * weights).sum()
+
+    # ---- memory plan ---------------------------------------------------------------
+    # Everything the runner keeps in HBM beyond the model is bounded by what is free when the plan is made:
+    # the activation store (layer inputs of all calibration samples), the cached weight planes of the fused
+    # executor and the per-micro-batch workspace of a pass.  GRASP_B200_MEM_BUDGET_GB caps the whole process
+    # (torch-allocated bytes) below the physical memory -- used by the tests to force the bounded paths.
+    def available_bytes(self, device) -> int:
+        """Bytes this process may still allocate on `device` (free + torch's cached-but-unused blocks)."""
+        device = torch.device(device)
+        if device.type != "cuda":
+            return 1 << 62
+        free, _ = torch.cuda.mem_get_info(device)
+        st = torch.cuda.memory_stats(device)
+        allocated = st.get("allocated_bytes.all.current", 0)
+        avail = free + st.get("reserved_bytes.all.current", 0) - allocated
+        cap = self.budget_bytes
+        if cap is not None:
+            avail = min(avail, cap - allocated)
+        return max(int(avail), 0)
+
+    def _linear_weight_bytes(self) -> int:
+        """fp32 bytes of every linear the fused executor keeps planes of (two fp16 planes = the same bytes)."""
+        total = 0
+        for p in list(self.layers.parameters()) + list(self.head.parameters()):
+            if p.dim() == 2:
+                total += p.numel() * 4
+        return total
+
+    def plan_store(self, calib: "CalibrationSet", hidden_shape, element_size: int) -> int:
+        """Fix the byte budget of the activation store for this calibration set (once per set): half of what
+        is free after the weight planes the passes will build, at least one full-size entry."""
+        key = id(calib)
+        if self.store_key == key and self.store_budget is not None:
+            return self.store_budget
+        per = len(calib) * hidden_shape[1] * hidden_shape[2] * element_size
+        device = calib.input_ids.device
+        avail = self.available_bytes(device)
+        if device.type == "cuda" and self.use_fused and self.use_grasp_gemm:
+            cached = self._fused.be.cached_bytes() if (self._fused is not None and hasattr(self._fused.be, "cached_bytes")) else 0
+            avail -= max(min(self._linear_weight_bytes(), self.plane_cap_bytes(device)) - cached, 0)
+        self.store_budget = max(int(0.5 * avail) if self.store_cap_bytes is None else self.store_cap_bytes, per)
+        self.store_key, self.store_per = key, per
+        return self.store_budget
+
+    def plane_cap_bytes(self, device) -> int:
+        """Upper bound of the cached weight planes: 35 % of the device, and never more than 40 % of the budget."""
+        total = torch.cuda.get_device_properties(device).total_memory
+        cap = int(0.35 * total)
+        if self.budget_bytes is not None:
+            cap = min(cap, int(0.4 * self.budget_bytes))
+        return cap
+
+    def _store_bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self.cache.values())
+
+    def pass_micro_batch(self, calib: "CalibrationSet", start_layer: int, hidden) -> int:
+        """Micro-batch of a sigma-gradient pass from `start_layer`: the configured one, shrunk when the state
+        the backward needs of layers [start_layer, L) would not fit in 70 % of what is free."""
+        mb = self.micro_batch
+        if not hidden.is_cuda:
+            return mb
+        cfg = self.hf.config
+        d, ff = hidden.shape[-1], getattr(cfg, "intermediate_size", 4 * hidden.shape[-1])
+        vocab = self.head.weight.shape[0]
+        S = hidden.shape[1]
+        per_sample = 4 * S * ((9 * d + 3 * ff) * (self.n_layers - start_layer) + 6 * ff + 2 * vocab + 4 * d)
+        avail = self.available_bytes(hidden.device)
+        fit = int(0.7 * avail // max(per_sample, 1))
+        return max(1, min(mb, fit))
 
     # ---- prefix cache -------------------------------------------------------------
     def invalidate_above(self, layer_id: int):
         """Layer `layer_id` changed: cached inputs of deeper layers are stale."""
-        for store in (self.cache, self.ckpt):
-            for k in [k for k in store if k > layer_id]:
-                del store[k]
+        for k in [k for k in self.cache if k > layer_id]:
+            del self.cache[k]
         if self._fused is not None and hasattr(self._fused.be, "drop_weights"):
             self._fused.be.drop_weights(layer_id)          # its modules were replaced: cached planes are stale
 
-    def build_cache(self, calib: CalibrationSet, layer_ids):
+    def invalidate_all(self):
+        """The layer list itself changed (layers removed): nothing cached can be trusted."""
+        self.cache, self.cache_key = {}, None
+        self.store_key = self.store_budget = None
+        if self._fused is not None and hasattr(self._fused.be, "drop_weights"):
+            self._fused.be.drop_weights(None)
+
+    def build_cache(self, calib: CalibrationSet, layer_ids, keep_only: bool = False):
+        """Make the input of the layers in `layer_ids` resident for all calibration samples -- as many of them
+        as the store budget holds (evenly spaced, always the lowest one); the others are recomputed from the
+        nearest resident entry below when their pass starts (sigma_gradients calls this with one layer).
+        Sources are whatever valid entries the store already has (checkpoints of the scoring pass, earlier
+        entries), else the embeddings.  keep_only drops every entry that is not in `layer_ids` afterwards."""
         if self.cache_key != id(calib):
             self.cache, self.cache_key = {}, id(calib)
-        need = sorted(set(l for l in layer_ids if l not in self.cache))
-        if not need:
-            return
-        n = len(calib)
-        # start from the deepest activation checkpoint left by the layer-scoring pass (if any)
-        ckpt = self.ckpt if self.ckpt_key == id(calib) else {}
-        starts = [c for c in ckpt if c <= need[0]]
-        start = max(starts) if starts else None
-        with torch.no_grad(), grasp_linear(self.use_grasp_gemm):
-            fused = None
-            for s in range(0, n, self.micro_batch):
-                ids = calib.input_ids[s:s + self.micro_batch]
-                if start is None:
-                    hidden, first = self.embed(ids), 0
+        wanted = sorted(set(layer_ids))
+        need = [l for l in wanted if l not in self.cache]
+        if need:
+            n = len(calib)
+            probe = self.embed(calib.input_ids[:1])
+            budget = self.plan_store(calib, probe.shape, probe.element_size())
+            per = self.store_per
+            slots = max(int((budget - self._store_bytes()) // max(per, 1)), 1)
+            if len(need) > slots:
+                # not all fit: keep slots-1 of them (one slot stays free for the entry recomputed per pass)
+                m = max(slots - 1, 1)
+                if m == 1:
+                    need = [need[0]]
                 else:
-                    hidden, first = ckpt[start][s:s + ids.shape[0]], start
-                position_ids, pos_emb = self._pos(hidden)
-                if s == 0:
-                    fused = self.fused(hidden)
-                for i in range(first, need[-1] + 1):
-                    if i in need:
-                        if i not in self.cache:
-                            self.cache[i] = torch.empty((n,) + tuple(hidden.shape[1:]), dtype=hidden.dtype,
-                                                        device=hidden.device)
-                        self.cache[i][s:s + ids.shape[0]] = hidden
-                    if i < need[-1]:
-                        if fused is not None:
-                            B, S, d = hidden.shape
-                            hidden = fused.layer_fwd(i, hidden.reshape(B * S, d), B, S, pos_emb[0], pos_emb[1],
-                                                     keep=False)[0].view(B, S, d)
-                        else:
-                            hidden = self._layer(i, hidden, position_ids, pos_emb)
-        self.ckpt, self.ckpt_key = {}, None      # checkpoints served their purpose: release the memory
+                    need = sorted({need[round(j * (len(need) - 1) / (m - 1))] for j in range(m)})
+            sources = [c for c in self.cache if c <= need[0]]
+            start = max(sources) if sources else None
+            with torch.no_grad(), grasp_linear(self.use_grasp_gemm):
+                fused = None
+                for s in range(0, n, self.micro_batch):
+                    ids = calib.input_ids[s:s + self.micro_batch]
+                    if start is None:
+                        hidden, first = self.embed(ids), 0
+                    else:
+                        hidden, first = self.cache[start][s:s + ids.shape[0]], start
+                    position_ids, pos_emb = self._pos(hidden)
+                    if s == 0:
+                        fused = self.fused(hidden)
+                    for i in range(first, need[-1] + 1):
+                        if i in need:
+                            if i not in self.cache:
+                                self.cache[i] = torch.empty((n,) + tuple(hidden.shape[1:]), dtype=hidden.dtype,
+                                                            device=hidden.device)
+                            self.cache[i][s:s + ids.shape[0]] = hidden
+                        if i < need[-1]:
+                            if fused is not None:
+                                B, S, d = hidden.shape
+                                hidden = fused.layer_fwd(i, hidden.reshape(B * S, d), B, S, pos_emb[0], pos_emb[1],
+                                                         keep=False)[0].view(B, S, d)
+                            else:
+                                hidden = self._layer(i, hidden, position_ids, pos_emb)
+        if keep_only:
+            for k in [k for k in self.cache if k not in wanted]:
+                del self.cache[k]      # checkpoints of the scoring pass served their purpose
 
     def _plan_checkpoints(self, calib: CalibrationSet, hidden_shape, element_size):
-        """Layers whose input is kept during the scoring pass: as many evenly spaced ones as fit in a
-        third of the free device memory (the selected layers are unknown until scoring has finished)."""
+        """Layers whose input is kept during the scoring pass: as many evenly spaced ones as fit in 40 % of
+        the store budget (the selected layers are unknown until scoring has finished)."""
         if not calib.input_ids.is_cuda:
             return []
-        per = len(calib) * hidden_shape[1] * hidden_shape[2] * element_size
-        free, _ = torch.cuda.mem_get_info(calib.input_ids.device)
-        count = int(min(self.n_layers - 1, (free // 3) // max(per, 1)))
+        budget = self.plan_store(calib, hidden_shape, element_size)
+        count = int(min(self.n_layers - 1, (0.4 * budget) // max(self.store_per, 1)))
         if count <= 0:
             return []
         stride = -(-self.n_layers // (count + 1))
@@ -420,7 +553,7 @@ class LlamaRunner:
 
     # ---- stage 1 ------------------------------------------------------------------
     def block_influence(self, calib: CalibrationSet, scorer: "BlockInfluence"):
-        self.ckpt, self.ckpt_key = {}, id(calib)
+        self.cache, self.cache_key = {}, id(calib)
         plan = None
         with torch.no_grad(), grasp_linear(self.use_grasp_gemm):
             fused = self.fused(self.embed(calib.input_ids[:1])) if len(calib) else None
@@ -430,10 +563,10 @@ class LlamaRunner:
                 if plan is None:
                     plan = self._plan_checkpoints(calib, states[0].shape, states[0].element_size())
                     for l in plan:
-                        self.ckpt[l] = torch.empty((len(calib),) + tuple(states[0].shape[1:]), dtype=states[0].dtype,
-                                                   device=states[0].device)
+                        self.cache[l] = torch.empty((len(calib),) + tuple(states[0].shape[1:]), dtype=states[0].dtype,
+                                                    device=states[0].device)
                 for l in plan:
-                    self.ckpt[l][s:s + ids.shape[0]] = states[l]     # states[l] is the input of layer l
+                    self.cache[l][s:s + ids.shape[0]] = states[l]     # states[l] is the input of layer l
                 # the reference adds one mean per DataLoader batch: sum_s w_s * mean_t(sample s)
                 w = calib.weights[s:s + ids.shape[0]]
                 if bool((w == w[0]).all()):
@@ -448,19 +581,20 @@ class LlamaRunner:
         self.build_cache(calib, [start_layer])
         src = self.cache[start_layer]
         fused = self.fused(src)
+        mb = self.pass_micro_batch(calib, start_layer, src)
+        self.last_pass_micro_batch = mb
         if fused is not None:
             with deferred_sigma_grads(layers.values()), torch.no_grad():
-                for s in range(0, len(calib), self.micro_batch):
-                    fused.forward_backward(src[s:s + self.micro_batch], calib.labels[s:s + self.micro_batch],
-                                           calib.weights[s:s + self.micro_batch], start_layer, start_layer)
+                for s in range(0, len(calib), mb):
+                    fused.forward_backward(src[s:s + mb], calib.labels[s:s + mb], calib.weights[s:s + mb],
+                                           start_layer, start_layer)
                 grads = {name: contract_sigma_grad(layer) for name, layer in layers.items()}
             dist.all_reduce_sum_many_(list(grads.values()))
             return grads
         with deferred_sigma_grads(layers.values()), grasp_linear(self.use_grasp_gemm):
-            for s in range(0, len(calib), self.micro_batch):
-                hidden = self.run_layers(src[s:s + self.micro_batch], start_layer, self.n_layers)
-                loss = self.loss_sum(hidden, calib.labels[s:s + self.micro_batch],
-                                     calib.weights[s:s + self.micro_batch])
+            for s in range(0, len(calib), mb):
+                hidden = self.run_layers(src[s:s + mb], start_layer, self.n_layers)
+                loss = self.loss_sum(hidden, calib.labels[s:s + mb], calib.weights[s:s + mb])
                 loss.backward()
             grads = {name: contract_sigma_grad(layer) for name, layer in layers.items()}
         # multi-GPU: each rank contracted the G of its own samples; dL/dS is linear in G

@@ -38,11 +38,15 @@ from . import _lib, ops
 class CudaBackend:
     """The product arithmetic: libgrasp_b200.so through grasp_b200.ops."""
 
-    def __init__(self, weight_cache_bytes: Optional[int] = None):
+    def __init__(self, weight_cache_bytes: Optional[int] = None, cap_fn=None):
         self._w = OrderedDict()       # (data_ptr, shape) -> Operand (holds a reference to the weight)
         self._w_bytes = 0
         self._w_cap = weight_cache_bytes
+        self._cap_fn = cap_fn         # device -> byte cap, asked once (the runner's memory plan)
         self._tags = {}
+
+    def cached_bytes(self) -> int:
+        return self._w_bytes
 
     # -- operands
     def prep(self, x):
@@ -57,8 +61,10 @@ class CudaBackend:
         if op is not None:
             self._drop(key)
         if self._w_cap is None:
-            total = torch.cuda.get_device_properties(w.device).total_memory
-            self._w_cap = int(0.35 * total)
+            if self._cap_fn is not None:
+                self._w_cap = int(self._cap_fn(w.device))
+            else:
+                self._w_cap = int(0.35 * torch.cuda.get_device_properties(w.device).total_memory)
         op = ops.split_f16(w.detach(), _lib.SCALE_TENSOR, keep_src=True)
         self._tags[key] = tag
         self._w[key] = op
@@ -198,7 +204,8 @@ class FusedLlama:
         # the runner owns this object: a proxy avoids a reference cycle that would keep the cached weight
         # planes (as large as the model) alive until the cycle collector runs
         self.r = weakref.proxy(runner)
-        self.be = backend if backend is not None else CudaBackend()
+        proxy = self.r                 # (a bound method would re-create the reference cycle)
+        self.be = backend if backend is not None else CudaBackend(cap_fn=lambda dev: proxy.plane_cap_bytes(dev))
 
     def supported(self) -> bool:
         r = self.r

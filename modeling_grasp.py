@@ -176,7 +176,7 @@ class GRASPModel(nn.Module):
         calib = self._calibration_set(calibration_dataloader, device)
         if not calib.supported:
             return False
-        runner.build_cache(calib, list(layers_id))
+        runner.build_cache(calib, list(layers_id), keep_only=True)
         return True
 
     # ------------------------------------------------------------------ misc (API parity)
@@ -256,6 +256,9 @@ class GRASPModel(nn.Module):
                 layers_to_remove = np.argsort(scores)[:num_prune_layers].tolist()
         if layers_to_remove is None:
             raise NotImplementedError("lack layers_to_remove")
+        if self._runner is not None:
+            self._runner.invalidate_all()      # cached layer inputs / weight planes are keyed by layer position
+        self._calib = None
         for layer_idx in sorted(layers_to_remove, reverse=True):
             try:
                 del self.model.model.layers[layer_idx]
@@ -278,6 +281,31 @@ class GRASPModel(nn.Module):
                 weights.append(module.weight.data.to(device=device))
         for name, usv in zip(names, engine.batched_svd(weights)):
             self._svd_cache[name] = usv
+
+    def svd_hoist_layers(self, layers_id: List[int], names_of, device="cuda") -> int:
+        """How many of the leading layers of `layers_id` to factor in one batched call: their factors
+        (U, S, Vh fp32) must fit in a quarter of what is free on the device; at least one layer.
+        names_of(layer_id) -> target module names of that layer."""
+        if not layers_id:
+            return 0
+        runner = self._engine_runner()
+        dev = torch.device(device)
+        if runner is None or dev.type != "cuda":
+            return len(layers_id)
+        avail = runner.available_bytes(dev)
+        used, count = 0, 0
+        for layer_id in layers_id:
+            need = 0
+            for name in names_of(layer_id):
+                w = self.model.get_submodule(name).weight
+                o, i = w.shape
+                r = min(o, i)
+                need += 4 * (o * r + r + r * i)
+            if count and used + need > 0.25 * avail:
+                break
+            used += need
+            count += 1
+        return engine.dist.all_min_int(count, dev)       # every rank must hoist the same matrices
 
     def replace_with_GRASPLayer(self, target_layer: str, device: Literal["cuda", "cpu"] = "cuda",
                                 log_file: Optional[str] = None):

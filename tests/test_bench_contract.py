@@ -22,7 +22,9 @@ def test_reference_arm_prints_the_contract_line():
     cb = line["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": "matrices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "NUM_PRUNE_LAYERS=2" in line["config"]["workload"] and line["config"]["extrapolated"] is True
+    # the workload is BASELINE configs[1] whatever --steps is; ms_per_step is what was timed, value the job's metric
+    assert "NUM_PRUNE_LAYERS=8" in line["config"]["workload"] and line["config"]["extrapolated"] is True
+    assert line["ms_per_step"] < 120e3 and line["config"]["extrapolated_job_s"] > 0
 
 
 def test_other_ranks_of_the_reference_arm_exit_quietly():

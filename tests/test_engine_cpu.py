@@ -61,11 +61,11 @@ def test_cache_from_checkpoint_matches_cache_from_scratch():
     calib = engine.CalibrationSet(synth.calibration_dataloader(5, 12, 256, seed=3), "cpu")
     with torch.no_grad():
         states = runner.hidden_states(calib.input_ids)
-    runner.ckpt, runner.ckpt_key = {2: states[2].clone()}, id(calib)     # as left by the scoring pass
-    runner.build_cache(calib, [2, 3])
+    runner.cache, runner.cache_key = {1: states[1].clone(), 2: states[2].clone()}, id(calib)   # as left by the scoring pass
+    runner.build_cache(calib, [2, 3], keep_only=True)
     assert torch.allclose(runner.cache[2], states[2], atol=1e-6)
     assert torch.allclose(runner.cache[3], states[3], atol=1e-5)
-    assert runner.ckpt == {}
+    assert set(runner.cache) == {2, 3}                                   # the unselected checkpoint was released
     runner.cache = {}
     runner.build_cache(calib, [1])                                       # no usable checkpoint: from the embeddings
     assert torch.allclose(runner.cache[1], states[1], atol=1e-5)
@@ -80,3 +80,41 @@ def test_perplexity_evaluator_matches_reference_formula():
     ref = restate.perplexity(model, tok)
     assert abs(evaluate.evaluate_perplexity(model, tok, None, "cpu", micro_batch=2) - ref) / ref < 1e-5
     assert abs(evaluate.evaluate_perplexity(model, tok, 2, "cpu") - restate.perplexity(model, tok[:2])) / ref < 1e-5
+
+
+def test_bounded_store_keeps_a_subset_and_recomputes_the_rest():
+    """With a store budget of three entries, build_cache keeps the lowest + evenly spaced layers and the
+    missing ones are recomputed from the nearest resident entry below when their pass asks for them."""
+    model = synth.random_llama("small", seed=6)                          # 6 layers
+    runner = engine.LlamaRunner(model, micro_batch=2, use_grasp_gemm=False)
+    calib = engine.CalibrationSet(synth.calibration_dataloader(4, 10, 1024, seed=4), "cpu")
+    with torch.no_grad():
+        states = runner.hidden_states(calib.input_ids)
+    per = states[0].numel() * 4
+    runner.store_key, runner.store_budget, runner.store_per = id(calib), 3 * per, per
+    runner.build_cache(calib, [1, 2, 3, 4, 5], keep_only=True)
+    assert set(runner.cache) == {1, 5}                                   # 3 slots: two kept, one free for a pass
+    runner.invalidate_above(4)                                           # layer 5 done, layer 4 is next
+    runner.build_cache(calib, [4])
+    assert set(runner.cache) == {1, 4}
+    assert torch.allclose(runner.cache[4], states[4], atol=1e-5)
+    runner.invalidate_above(3)
+    runner.build_cache(calib, [3])
+    assert torch.allclose(runner.cache[3], states[3], atol=1e-5)
+
+
+def test_runner_refuses_other_model_families_and_masked_labels_average_like_hf():
+    from transformers import MistralConfig, MistralForCausalLM
+    cfg = MistralConfig(hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=4,
+                        num_key_value_heads=2, vocab_size=64, sliding_window=8)
+    assert not engine.LlamaRunner.supports(MistralForCausalLM(cfg))      # sliding window: generic path
+    model = synth.random_llama("tiny", seed=3)
+    runner = engine.LlamaRunner(model, micro_batch=2, use_grasp_gemm=False)
+    tokens = synth.random_tokens(2, 16, 256, seed=5)
+    ids, labels = tokens[:, :-1], tokens[:, 1:].clone()
+    labels[0, 5:] = -100                                                 # padded tail, ignored by HF's loss
+    with torch.no_grad():
+        hidden = runner.run_layers(runner.embed(ids), 0, runner.n_layers)
+        ours = runner.loss_sum(hidden, labels, torch.ones(2))
+        ref = sum(model(input_ids=ids[i:i + 1], labels=labels[i:i + 1], use_cache=False)[0].item() for i in range(2))
+    assert abs(ours.item() - ref) < 1e-4
