@@ -46,6 +46,8 @@ def parse():
     p.add_argument("--steps", type=int, default=8, help="pruned layers compressed in the timed region (8 = one job)")
     p.add_argument("--job-layers", type=int, default=JOB_LAYERS, help="NUM_PRUNE_LAYERS of the job (configs[1]: 8)")
     p.add_argument("--no-library-baseline", action="store_true")
+    p.add_argument("--save-kept", default="", help="write the retained index sets + scores of the first execution (N=1 reference for the N>1 runs)")
+    p.add_argument("--kept-reference", default=os.path.join(ROOT, "profiles", "r02_kept_indices_llama2-7b_1gpu.pt"))
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", choices=["ours", "reference"], default="ours")
     p.add_argument("--model", default="llama2-7b")
@@ -372,9 +374,13 @@ def run_ours(a):
     picked = []                       # every block's retained index sets (device tensors until the read-back)
     select = gm.dynamic_svd_selection
 
-    def spy(*args, **kw):
-        out = select(*args, **kw)
+    score_inputs = []                 # (name, sigma-gradient, singular values) per matrix of the FIRST execution
+
+    def spy(grads, *args, **kw):
+        out = select(grads, *args, **kw)
         picked.append(dict(out))
+        if not job_ms:                # references only, no kernels: the scores are formed after the timing
+            score_inputs.extend((n, grads[n], gm.model.get_submodule(n).S.data) for n in grads)
         return out
     gm.dynamic_svd_selection = spy
 
@@ -382,6 +388,7 @@ def run_ours(a):
     clocks = ClockSampler(local_rank)
     launches0 = ops.launch_count()
     job_ms, job_resident_ms, job_layers_done, d2h_bytes, checksums, layers_chosen = [], [], [], 0, [], None
+    first_kept = None
     micro_batch, pass_mb = None, None
     remaining = a.steps
     clocks.start()
@@ -413,6 +420,8 @@ def run_ours(a):
         d2h_bytes += sum(v.numel() * 8 for blk in kept for v in blk.values()) + len(importances) * 8
         flat = {k: v for blk in kept for k, v in blk.items()}
         checksums.append(int(sum(int(flat[k].sum()) * (i + 1) for i, k in enumerate(sorted(flat)))))
+        if len(job_ms) == 1:
+            first_kept = flat
         if n == a.job_layers or layers_chosen is None:
             layers_chosen = list(gm.redundant_layers)
         micro_batch = gm._runner.micro_batch if gm._runner else a.micro_batch
@@ -481,6 +490,31 @@ def run_ours(a):
                 "memory": {"peak_allocated_gb": round(torch.cuda.max_memory_allocated() / 2**30, 1),
                            "peak_reserved_gb": round(torch.cuda.max_memory_reserved() / 2**30, 1),
                            "alloc_retries": torch.cuda.memory_stats().get("num_alloc_retries", 0)}}
+        # retained index sets against the committed single-GPU run of the same job: they may differ only at ties
+        # (multi-GPU changes the order of the fp32 sums), i.e. a swapped index scores within a hair of the k-th score
+        scores = {n: (g * S).abs().cpu() for n, g, S in score_inputs}
+        if a.save_kept and job_layers_done[0] == a.job_layers:
+            torch.save({"workload": workload_name(a), "n_gpus": world, "kept": first_kept,
+                        "scores": {n: v.half() for n, v in scores.items()}}, a.save_kept)
+        if os.path.exists(a.kept_reference) and job_layers_done[0] == a.job_layers:
+            try:
+                refk = torch.load(a.kept_reference, map_location="cpu", weights_only=False)
+                if refk.get("workload") == workload_name(a):
+                    jmin, swapped, tie, total = 1.0, 0, 0.0, 0
+                    for n, theirs in refk["kept"].items():
+                        ours_set, theirs_set = set(first_kept[n].tolist()), set(theirs.tolist())
+                        total += len(theirs_set)
+                        jmin = min(jmin, len(ours_set & theirs_set) / max(len(ours_set | theirs_set), 1))
+                        kth = scores[n][first_kept[n][-1]].item()
+                        for i in ours_set ^ theirs_set:
+                            swapped += 1
+                            tie = max(tie, abs(scores[n][i].item() - kth) / max(kth, 1e-30))
+                    line["config"]["index_sets_vs_1gpu_run"] = {
+                        "reference": os.path.relpath(a.kept_reference, ROOT), "matrices": len(refk["kept"]),
+                        "min_jaccard": jmin, "swapped_indices": swapped // 2, "of": total,
+                        "worst_tie_margin_of_kth_score": tie}
+            except Exception as exc:
+                line["config"]["index_sets_vs_1gpu_run"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
         if not a.no_library_baseline:
             try:
                 line["library_baseline"] = gpu_library_sample(a, model, dev)

@@ -29,3 +29,22 @@ def cuda():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+# Measured parity figures (Jaccard of index sets, tie margins, sigma / Frobenius errors) are collected here and
+# printed in the terminal summary, so that they are in the log of a plain `pytest -q` run even when every test passes.
+_PARITY_LINES = []
+
+
+@pytest.fixture
+def parity_log():
+    def log(line: str):
+        _PARITY_LINES.append(line)
+    return log
+
+
+def pytest_terminal_summary(terminalreporter):
+    if _PARITY_LINES:
+        terminalreporter.write_sep("-", "measured parity against the oracle")
+        for line in _PARITY_LINES:
+            terminalreporter.write_line(line)

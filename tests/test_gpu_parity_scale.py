@@ -1,0 +1,103 @@
+"""GPU: parity with the oracle (oracle/restate.py = the reference's torch CPU path) at BASELINE-scale sizes.
+
+  * single matrices of TinyLlama / LLaMA-2-7B shape (2048x2048, 5632x2048, 4096x4096): singular values, retained
+    index set (Jaccard + tie margins), score error, rebuilt-weight Frobenius error on the SAME index set;
+  * the whole path on a 2-layer model of TinyLlama-1.1B widths (configs[0] shapes) with 4 calibration samples.
+
+The measured figures are printed in the terminal summary (tests/conftest.py)."""
+import copy
+
+import pytest
+import torch
+
+from grasp_b200 import synth
+from oracle import restate
+from parity_util import compare_blocks, compare_final_weights, jaccard, rel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("shape", [(2048, 2048), (5632, 2048), (4096, 4096)])
+def test_matrix_pipeline_matches_oracle(cuda, parity_log, shape):
+    from grasp_b200 import ops
+    out_f, in_f = shape
+    g = torch.Generator().manual_seed(out_f + in_f)
+    W = torch.randn(out_f, in_f, generator=g) * 0.02
+    G = torch.randn(out_f, in_f, generator=g)
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    # oracle: reference modeling_grasp.py:231 (svd), :354-363 via the dS = diag(U^T G V) identity, :392-404, :454
+    U0, S0, Vh0 = restate.svd(W)
+    g0 = restate.sigma_grad_from_G(U0, G, Vh0)
+    sc0 = restate.importance(g0, S0, "taylor")
+    k = restate.preserve_rank(in_f, out_f, 0.9)
+    idx0 = torch.topk(sc0, k).indices
+    W0 = restate.merged_weight(U0, S0, Vh0, idx0)
+    # CUDA path through the C ABI
+    U, S, Vh = ops.svd(W.to(cuda))
+    gs, score = ops.sigma_score(U, G.to(cuda), Vh, S, metric="taylor")
+    idx = ops.topk(score, k)
+    W_same = ops.lowrank_rebuild(U, S, Vh, idx0.to(cuda))            # same retained set as the oracle
+    in_w, out_w = ops.factor_pack(U, S, Vh, idx0.to(cuda))
+    torch.cuda.synchronize()
+
+    sig = ((S.cpu() - S0).abs().max() / S0[0]).item()
+    big = S0 >= 1e-3 * S0[0]
+    sig_rel = ((S.cpu() - S0).abs()[big] / S0[big]).max().item()
+    jac = jaccard(idx.tolist(), idx0.tolist())
+    kth = sc0[idx0[-1]].item()
+    swapped = set(idx.tolist()) ^ set(idx0.tolist())
+    tie = max((abs(sc0[i].item() - kth) / kth for i in swapped), default=0.0)
+    sc_err = ((score.cpu() - sc0).abs().max() / sc0.max()).item()
+    fro = (torch.linalg.norm(W_same.cpu().double() - W0.double()) / torch.linalg.norm(W0.double())).item()
+    fro_f = (torch.linalg.norm((out_w @ in_w).cpu().double() - W0.double()) / torch.linalg.norm(W0.double())).item()
+    parity_log(f"matrix {out_f}x{in_f} k={k}: sigma {sig:.1e} of sigma_max (per value {sig_rel:.1e}), Jaccard {jac:.4f} "
+               f"({len(swapped) // 2} swapped, tie margin {100 * tie:.3f} %), score error {sc_err:.1e}, rebuilt weight "
+               f"{fro:.1e} (factor pair {fro_f:.1e}) relative Frobenius")
+    assert sig < 1e-5 and sig_rel < 1e-4                                # north-star bar: 1e-4 relative
+    assert jac >= 0.97 and tie <= 0.02
+    assert sc_err < 2e-2
+    if fro >= 1e-3:                                                      # near-degenerate pair across the cut:
+        U64, S64, Vh64 = torch.linalg.svd(W.double(), full_matrices=False)   # be as close to the truth as LAPACK is
+        Wt = (U64[:, idx0] * S64[idx0]) @ Vh64[idx0]
+        e_o = (torch.linalg.norm(W_same.cpu().double() - Wt) / torch.linalg.norm(Wt)).item()
+        e_r = (torch.linalg.norm(W0.double() - Wt) / torch.linalg.norm(Wt)).item()
+        parity_log(f"matrix {out_f}x{in_f}: against fp64 truth ours {e_o:.1e}, oracle {e_r:.1e}")
+        assert e_o <= max(1e-3, 3 * e_r)
+    assert abs(fro - fro_f) < 1e-4
+
+
+def test_two_layer_tinyllama_width_end_to_end(cuda, parity_log):
+    """configs[0] shapes (hidden 2048, MLP 5632, 32 heads / 4 kv heads, vocab 32000), 2 layers, 4 samples x 64 tokens."""
+    import grasp
+    from modeling_grasp import GRASPModel
+    model = synth.random_llama("tinyllama-1.1b", seed=5, num_hidden_layers=2)
+    tokens = synth.random_tokens(4, 64, model.config.vocab_size, seed=6)
+    dense = copy.deepcopy(model)
+    oracle_model = copy.deepcopy(model)
+    ref = restate.run_grasp(oracle_model, tokens, num_prune_layers=2, compression_ratio=0.9)
+    ref_sd = {k: v.detach() for k, v in oracle_model.state_dict().items()}
+    ppl_ref = restate.perplexity(oracle_model, tokens)
+
+    gm = GRASPModel(model.to(cuda))
+    rec = {"blocks": []}
+    select = gm.dynamic_svd_selection
+
+    def spy(grads, **kw):
+        names = list(grads.keys())
+        S = {n: gm.model.get_submodule(n).S.data.clone() for n in names}
+        idx = select(grads, **kw)
+        rec["blocks"].append({"names": names, "S": S, "grads": {n: grads[n].clone() for n in names},
+                              "indices": {n: torch.as_tensor(idx[n]).clone() for n in names}})
+        return idx
+    gm.dynamic_svd_selection = spy
+    dl = synth.calibration_dataloader(0, 0, 0, tokens=tokens)
+    grasp.compress(gm, dl, num_prune_layers=2, compression_ratio=0.9, device=cuda)
+    assert gm.redundant_layers == ref["layers_id"]
+    assert rel(gm.layer_importances, ref["layer_importances"]) < 1e-4
+    tag = "e2e tinyllama-width 2 layers"
+    compare_blocks(rec, ref, parity_log, tag)
+    ours_sd = {k: v.detach().cpu() for k, v in gm.model.state_dict().items()}
+    compare_final_weights(rec, ref, ours_sd, ref_sd, dense.state_dict(), parity_log, tag)
+    ppl = restate.perplexity(gm.model.to("cpu"), tokens)
+    parity_log(f"{tag}: perplexity {ppl:.4f} vs oracle {ppl_ref:.4f} ({100 * abs(ppl - ppl_ref) / ppl_ref:.4f} %)")
+    assert abs(ppl - ppl_ref) / ppl_ref < 5e-3
