@@ -27,6 +27,16 @@ elif what == "planes":
         xo, wo, dyo = ops.split_f16(x), ops.split_f16(w, _lib.SCALE_TENSOR), ops.split_f16(dy)
         ops.gemm_planes(xo, wo)                 # x W^T   (K-major B)
         ops.gemm_planes(dyo, wo, b_kn=True)     # dy W    (MN-major B)
+elif what == "shortk":
+    # the rank-k GEMMs of a compressed layer: t[T,k] * OutW[11008,k]^T (short K) and x[T,4096] * InW[k,4096]^T (skinny N)
+    from grasp_b200 import _lib
+    T = 8176
+    t_ = torch.randn(T, 298, device=dev); w = torch.randn(11008, 298, device=dev) * 0.02
+    x = torch.randn(T, 4096, device=dev); wi = torch.randn(204, 4096, device=dev) * 0.02
+    to, wo, xo, wio = ops.split_f16(t_), ops.split_f16(w, _lib.SCALE_TENSOR), ops.split_f16(x), ops.split_f16(wi, _lib.SCALE_TENSOR)
+    for _ in range(3):
+        ops.gemm_planes(to, wo)
+        ops.gemm_planes(xo, wio)
 elif what == "rowops":
     T = 8176
     x = torch.randn(T, 4096, device=dev); w = torch.ones(4096, device=dev)

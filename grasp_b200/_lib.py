@@ -9,6 +9,7 @@ _LIB = None
 _LIB_PATH = Path(__file__).resolve().parent / "libgrasp_b200.so"
 
 PREC_SIMT, PREC_BF16X3, PREC_BF16X6, PREC_F16X3 = 0, 3, 6, 16
+SVD_NO_PRECOND = 0x100          # flag for grasp_svd_batched's prec (include/grasp_b200.h)
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 METRIC_GRADIENT, METRIC_TAYLOR = 0, 1
 SCALE_ROWS, SCALE_TENSOR = 0, 2

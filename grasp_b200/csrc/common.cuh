@@ -75,6 +75,9 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+// Row pitch (elements) of a 16-bit operand plane: whole 128-byte lines, so that the 64-element row segments the TMA
+// boxes fetch never straddle a line (at the rank-k widths 204 / 298 a pitch rounded to 8 made every segment touch two)
+inline __host__ __device__ int64_t plane_pitch(int64_t cols) { return (cols + 63) / 64 * 64; }
 
 // number of SMs of the current device (cached)
 int sm_count();

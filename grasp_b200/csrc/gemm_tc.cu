@@ -45,7 +45,24 @@ struct TcParams {
   const float* inv_sa;  // F16 planes: per-row inverse scale of A (M) and B (N); the accumulator is
   const float* inv_sb;  //   multiplied by inv_sa[m] * inv_sb[n] before the epilogue
   int kgroup;           // K blocks accumulated in one TMEM buffer before the epilogue drains it (0 = 1)
+  int group_m;          // tile rasterisation: M blocks per super-row (see tile_coords)
+  int staged;           // EPI_STORE fp32: transpose through shared memory, 128-byte row segments per store
 };
+
+// Tile order of the persistent loop.  Consecutive tile indices run at the same time on different SMs, so they
+// should share operand rows: tiles are walked in super-rows of `group_m` M blocks, M fastest inside a super-row,
+// then along N.  The A rows of a super-row (group_m x 128 x K planes) stay in L2 while the B tiles stream past
+// once per super-row.  M-fastest over ALL M blocks (the round-1 order) re-read every A tile once per wave:
+// ncu counted 3.17 GB of DRAM traffic for 0.68 GB of operands + output (profiles/r01_ncu_traffic.json).
+__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int group_m, int& m_blk, int& n_blk) {
+  const int per_group = group_m * tiles_n;
+  const int g = tile / per_group;
+  const int first = g * group_m;
+  const int rows = min(group_m, tiles_m - first);     // the last super-row may be shorter
+  const int t = tile - g * per_group;
+  m_blk = first + t % rows;
+  n_blk = t / rows;
+}
 
 template <int NS, int BN>
 struct TcCfg {
@@ -54,7 +71,9 @@ struct TcCfg {
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;
   static constexpr int NACC = 512 / BN;       // ring of per-K-block accumulators in TMEM
   static constexpr int TMEM_COLS = 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 4 * BN * 4 /*sigma red*/ + 256;
+  // epilogue scratch: [4][BN] floats of the sigma reduction, or one 32 x 32 fp32 staging tile per epilogue warp
+  static constexpr int EPI_SMEM = (BN / 32) * 4096;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + EPI_SMEM + 256;
   static constexpr int EPI_THREADS = BN;      // 4 epilogue warps per 128 output columns (128 fp32 accumulators per thread)
   static constexpr int THREADS = 64 + EPI_THREADS;
   static_assert(STAGES >= 2, "need at least a double-buffered ring");
@@ -104,7 +123,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile % p.tiles_m) * TC_BM, n0 = (tile / p.tiles_m) * BN;
+        int m_blk, n_blk;
+        tile_coords(tile, p.tiles_m, p.tiles_n, p.group_m, m_blk, n_blk);
+        const int m0 = m_blk * TC_BM, n0 = n_blk * BN;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           unsigned char* sA = smem + stage * Cfg::STAGE_BYTES;
@@ -175,8 +196,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int half = (warp - 2) >> 2;               // which 128-column half of the tile this warp drains
     const int ep_tid = (int)threadIdx.x - 64;       // 0..EPI_THREADS-1
     int acc = 0; uint32_t acc_phase = 0;
+    float* stg = red + (warp - 2) * 1024;          // this warp's 32 x 32 staging tile (EPI_STORE)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_blk = tile % p.tiles_m, n_blk = tile / p.tiles_m;
+      int m_blk, n_blk;
+      tile_coords(tile, p.tiles_m, p.tiles_n, p.group_m, m_blk, n_blk);
       const int row = m_blk * TC_BM + quad * 32 + lane;
       const int n0 = n_blk * BN;
       float racc[128];
@@ -186,13 +209,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         mbar_wait(&acc_full[acc], acc_phase);
         tc_fence_after_sync();
         const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * 128);
+        if constexpr (BN == 128) {
+          // two TMEM loads in flight per wait (the second one's latency hides behind the first one's adds);
+          // the 320-thread BN = 256 variant has no registers to spare for it (168 per thread)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float t[32];
-          tmem_ld_32x32(t_row + (uint32_t)(c * 32), t);
-          tmem_ld_wait();
+          for (int c = 0; c < 4; c += 2) {
+            float t0[32], t1[32];
+            tmem_ld_32x32(t_row + (uint32_t)(c * 32), t0);
+            tmem_ld_32x32(t_row + (uint32_t)(c * 32 + 32), t1);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) racc[c * 32 + j] += t[j];   // round-to-nearest fp32 add
+            for (int j = 0; j < 32; ++j) racc[c * 32 + j] += t0[j];   // round-to-nearest fp32 add
+#pragma unroll
+            for (int j = 0; j < 32; ++j) racc[c * 32 + 32 + j] += t1[j];
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float t[32];
+            tmem_ld_32x32(t_row + (uint32_t)(c * 32), t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) racc[c * 32 + j] += t[j];   // round-to-nearest fp32 add
+          }
         }
         tc_fence_before_sync();
         mbar_arrive(&acc_empty[acc]);               // hand the TMEM buffer back to the MMA warp
@@ -212,7 +251,34 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         float* v = &racc[c * 32];
         const int col0 = n0 + half * 128 + c * 32;
         if constexpr (EPI == EPI_STORE) {
-          if (row < p.M && col0 < p.N) {
+          if (p.staged) {
+            // Each lane holds 32 consecutive columns of ITS row: stored directly, one instruction writes 16 bytes
+            // into 32 different rows (32 half-filled sectors).  Staged through shared memory (float4 chunks
+            // XOR-swizzled with the row, conflict-free both ways) the warp writes 4 rows x 128 contiguous bytes
+            // per instruction.  N % 4 == 0 here, so a float4 is inside or outside the matrix as a whole.
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(stg + lane * 32 + ((q ^ (lane & 7)) << 2)) =
+                  make_float4(p.alpha * v[4 * q], p.alpha * v[4 * q + 1], p.alpha * v[4 * q + 2], p.alpha * v[4 * q + 3]);
+            __syncwarp();
+            const int sub = lane >> 3, pos = lane & 7;
+            const int row_base = m_blk * TC_BM + quad * 32;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = i * 4 + sub;
+              const int col = col0 + ((pos ^ (r & 7)) << 2);
+              float4 o = *reinterpret_cast<const float4*>(stg + r * 32 + (pos << 2));
+              if (row_base + r < p.M && col < p.N) {
+                float* dst = static_cast<float*>(p.C) + (int64_t)(row_base + r) * p.ldc + col;
+                if (p.beta != 0.f) {
+                  const float4 old = *reinterpret_cast<const float4*>(dst);
+                  o.x += p.beta * old.x; o.y += p.beta * old.y; o.z += p.beta * old.z; o.w += p.beta * old.w;
+                }
+                *reinterpret_cast<float4*>(dst) = o;
+              }
+            }
+            __syncwarp();
+          } else if (row < p.M && col0 < p.N) {
             const int ncols = min(32, p.N - col0);
             if (p.c_bf16) {
               __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.C) + (int64_t)row * p.ldc + col0;
@@ -771,7 +837,7 @@ int tc_make_map_4d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1,
   return 0;
 }
 
-static int kp_of(int64_t K) { return (int)round_up(K, 8); }
+static int kp_of(int64_t K) { return (int)plane_pitch(K); }
 static size_t planes_bytes(int NS, int64_t R, int64_t K) { return round_up((int64_t)NS * R * kp_of(K) * 2, 1024); }
 static int ns_of(int prec) { return prec == GRASP_PREC_BF16X6 ? 3 : 2; }
 static bool is_f16(int prec) { return prec == GRASP_PREC_F16X3; }
@@ -817,7 +883,9 @@ static int split_operand_f16(const float* src, int64_t ld, int layout, int R, in
   return 0;
 }
 
-static int gemm_kgroup(int ns);
+static int gemm_kgroup(int ns, int K);
+static int raster_group_m(int tiles_m, int tiles_n, int K, int ns);
+static bool staged_epilogue();
 
 template <int NS, int BN, int EPI, int BMN = 0, int F16 = 0>
 static int launch_core(const __nv_bfloat16* Ap, const __nv_bfloat16* Bp, TcParams prm, void* stream) {
@@ -839,7 +907,10 @@ static int launch_core(const __nv_bfloat16* Ap, const __nv_bfloat16* Bp, TcParam
   }
   prm.tiles_m = (int)ceil_div(prm.M, TC_BM);
   prm.tiles_n = (int)ceil_div(prm.N, BN);
-  prm.kgroup = gemm_kgroup(NS);
+  prm.kgroup = gemm_kgroup(NS, prm.K);
+  prm.group_m = raster_group_m(prm.tiles_m, prm.tiles_n, prm.K, NS);
+  prm.staged = (EPI == EPI_STORE && !prm.c_bf16 && (prm.N & 3) == 0 && (prm.ldc & 3) == 0 &&
+                (reinterpret_cast<uintptr_t>(prm.C) & 15) == 0 && staged_epilogue()) ? 1 : 0;
   const int total = prm.tiles_m * prm.tiles_n;
   const int grid = total < sm_count() ? total : sm_count();
   GRASP_LAUNCH((tc_gemm_kernel<NS, BN, EPI, BMN, F16>), dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, mapA, mapB, prm);
@@ -874,11 +945,37 @@ static bool wide_tiles(int64_t M, int64_t N, int64_t K = 1 << 20) {
 // 8 blocks 1.9e-6 / -1.6e-6 at 0.634 ms (torch fp32 matmul: 3.5e-6, unbiased).  The drain is therefore NOT what
 // limits the kernel (3-5 %): at 410-430 TFLOP/s fp32-equivalent = 1.25-1.3 PFLOP/s of fp16 MMA it runs at the
 // power-capped sustained rate of the part.  Default 1 (accuracy first); GRASP_GEMM_KGROUP overrides.
-static int gemm_kgroup(int ns) {
-  static int v = -1;
+// Short K (the rank-k factors of compressed layers, K <= 512): a tile lives for <= 8 K blocks and its time is the
+// TMEM drain (128 x BN x 4 bytes at 64 B/clk per K block), ~2x the HBM-write bound of the output; two K blocks per
+// drain bring the drain under the write bound at 24 accumulations per chain (error class of the row above).
+static int gemm_kgroup(int ns, int K) {
+  static int v = -1, vs = -1;
   if (v < 0) { const char* e = getenv("GRASP_GEMM_KGROUP"); v = e ? atoi(e) : 0; }
+  if (vs < 0) { const char* e = getenv("GRASP_GEMM_KGROUP_SHORT"); vs = e ? atoi(e) : 2; }
   (void)ns;
-  return v > 0 ? v : 1;
+  if (v > 0) return v;
+  return (K <= 512 && vs > 0) ? vs : 1;
+}
+
+// M blocks per super-row of the tile order: as many as keep their A planes (128 x K x NS x 2 bytes each) within
+// ~24 MB of the 126 MB L2, at least 4, and a whole number of waves where possible.  GRASP_GEMM_GROUP_M overrides
+// (a value >= tiles_m restores the round-1 M-fastest order).
+static int raster_group_m(int tiles_m, int tiles_n, int K, int ns) {
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("GRASP_GEMM_GROUP_M"); forced = e ? atoi(e) : 0; }
+  if (forced > 0) return forced < tiles_m ? forced : tiles_m;
+  (void)tiles_n;
+  const double per_block = 128.0 * (double)kp_of(K) * ns * 2.0;
+  int g = (int)(24.0 * 1024 * 1024 / per_block);
+  if (g < 4) g = 4;
+  if (g > tiles_m) g = tiles_m;
+  return g;
+}
+
+static bool staged_epilogue() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GRASP_GEMM_STAGED"); v = e ? atoi(e) : 1; }
+  return v != 0;
 }
 
 static bool use_bmn() {

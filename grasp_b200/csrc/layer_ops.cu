@@ -385,7 +385,7 @@ extern "C" int grasp_rmsnorm_fwd(const float* x, const float* w, int64_t rows, i
   if (!aligned16(x) || !aligned16(w) || (y && !aligned16(y))) return bad_arg("rmsnorm_fwd: pointers must be 16-byte aligned");
   if (planes && (reinterpret_cast<uintptr_t>(planes) & 1023)) return bad_arg("rmsnorm_fwd: planes must be 1024-byte aligned");
   if (rows == 0) return 0;
-  const int64_t dp = round_up(d, 8);
+  const int64_t dp = plane_pitch(d);
   static size_t granted = 48 * 1024;
   int rc = row_smem_attr((const void*)rmsnorm_fwd_kernel, (size_t)dp * 4, granted, "rmsnorm_fwd attr");
   if (rc) return rc;
@@ -450,7 +450,7 @@ extern "C" int grasp_swiglu_fwd(const float* g, const float* u, int64_t rows, in
     return 0;
   }
   if (reinterpret_cast<uintptr_t>(planes) & 1023) return bad_arg("swiglu_fwd: planes must be 1024-byte aligned");
-  const int64_t cp = round_up(cols, 8);
+  const int64_t cp = plane_pitch(cols);
   if (cp * 4 > 200 * 1024) return bad_arg("swiglu_fwd: row too long for the fused operand form");
   static size_t granted = 48 * 1024;
   int rc = row_smem_attr((const void*)swiglu_fwd_rows_kernel, (size_t)cp * 4, granted, "swiglu_fwd attr");
@@ -480,7 +480,7 @@ extern "C" int grasp_swiglu_bwd(const float* dh, const float* g, const float* u,
   }
   if ((reinterpret_cast<uintptr_t>(dg_planes) & 1023) || (reinterpret_cast<uintptr_t>(du_planes) & 1023))
     return bad_arg("swiglu_bwd: planes must be 1024-byte aligned");
-  const int64_t cp = round_up(cols, 8);
+  const int64_t cp = plane_pitch(cols);
   if (cp * 8 > 200 * 1024) return bad_arg("swiglu_bwd: row too long for the fused operand form");
   static size_t granted = 48 * 1024;
   int rc = row_smem_attr((const void*)swiglu_bwd_rows_kernel, (size_t)cp * 8, granted, "swiglu_bwd attr");

@@ -103,9 +103,13 @@ __global__ void svd_init_kernel(const float* __restrict__ A, int64_t lda, int r,
 }
 
 // ---------------------------------------------------------------------------
-// gram: Gpart[pair][split] = Yp[:, kchunk] Yp[:, kchunk]^T   (64 x 64, fp32 FMA)
-// grid (nsplit, npairs, nmat)
+// gram: Gpart[pair][split] = Yp[:, kchunk] Yp[:, kchunk]^T   (64 x 64)
+// grid (nsplit, npairs, nmat).  ACC = float: fp32 FMA.  ACC = double (clean-up sweeps): the products of fp32
+// numbers are exact in fp64, so the Gram is exact for the rows as stored -- an fp32 sum over L ~ 4096..15000 terms
+// carries ~1e-6 |y_i||y_j| of noise, which forced a rotation threshold of 1e-6 and left neighbouring singular
+// vectors rotated by ~1e-6 sigma / (2 gap) ~ 2e-3 at n = 4096 (4x LAPACK's error in the rebuilt weights).
 // ---------------------------------------------------------------------------
+template <typename ACC>
 __global__ void __launch_bounds__(J_THREADS)
 svd_gram_kernel(SvdGroup g, int round) {
   const SvdMat& M = g.mat[blockIdx.z];
@@ -118,7 +122,7 @@ svd_gram_kernel(SvdGroup g, int round) {
   const int per = (chunks + g.nsplit - 1) / g.nsplit;
   const int c_beg = blockIdx.x * per, c_end = min(chunks, c_beg + per);
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  float acc[4][4] = {};
+  ACC acc[4][4] = {};
   for (int c = c_beg; c < c_end; ++c) {
     // 64 rows x 32 k: thread -> (row = e / 32, kk = e % 32): 128-byte coalesced row segments
 #pragma unroll
@@ -138,7 +142,10 @@ svd_gram_kernel(SvdGroup g, int round) {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) {
+          if constexpr (sizeof(ACC) == 8) acc[i][j] = fma((double)a[i], (double)b[j], acc[i][j]);
+          else acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
     }
     __syncthreads();
   }
@@ -146,7 +153,7 @@ svd_gram_kernel(SvdGroup g, int round) {
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) out[(ty * 4 + i) * JS + tx * 4 + j] = acc[i][j];
+    for (int j = 0; j < 4; ++j) out[(ty * 4 + i) * JS + tx * 4 + j] = (float)acc[i][j];
 }
 
 // ---------------------------------------------------------------------------
@@ -768,11 +775,186 @@ __global__ void svd_reopen_kernel(SvdGroup g) {
   }
 }
 
-__global__ void svd_info_kernel(const uint32_t* __restrict__ stats, int32_t* __restrict__ info) {
+__global__ void svd_info_kernel(const uint32_t* __restrict__ stats, const uint32_t* __restrict__ pre_fail,
+                                int32_t* __restrict__ info) {
   info[0] = (int32_t)stats[1];
-  info[1] = (int32_t)stats[0];
+  info[1] = (int32_t)(stats[0] && !(pre_fail && *pre_fail));   // converged, and the preconditioning (if any) was sound
   info[2] = (int32_t)stats[2];
   info[3] = (int32_t)stats[3];   // sweeps of the tensor-core phase (0 on the CUDA-core path)
+}
+
+// ---------------------------------------------------------------------------
+// CholeskyQR2 preconditioning of wide working matrices (L >= 1.5 r).
+// The Jacobi phase streams whole rows of Z = [Y | QT] through HBM once per round, so its time grows with the
+// row length L + r.  For Y0 (r x L) = Lm * Q with Q (r x L) of orthonormal rows, the SVD of the SQUARE
+// Lm = U S W^T gives Y0 = U S (W^T Q): the rounds run on rows of length 2 r instead of L + r and the long
+// dimension is touched only by a handful of tensor-core GEMMs (tc_gemm_f32, fp32-class arithmetic):
+//     G = Y0 Y0^T,  M1 = inv(chol(G)),  Q1 = M1 Y0,  G2 = Q1 Q1^T,  M2 = inv(chol(G2)),  Q = M2 Q1,  Lm = Y0 Q^T.
+// The inverse Cholesky factor is built recursively: for G = [[G11, .], [G21, G22]],
+//     M11 = invchol(G11), T = G21 M11^T, M22 = invchol(G22 - T T^T), M21 = -M22 T M11,
+// with 128 x 128 blocks solved by one CTA in shared memory.  A non-positive pivot or a Q that is not orthonormal
+// to 1e-4 (cond(Y0)^2 beyond fp32: does not happen for random-init weights, can for trained ones) sets a flag that
+// ends up in info[1] = 0, and the caller repeats the matrix with GRASP_SVD_NO_PRECOND.
+// ---------------------------------------------------------------------------
+constexpr int IC_BASE = 128;
+constexpr int IC_SMEM = 2 * IC_BASE * (IC_BASE + 1) * 4;
+
+// M = inv(chol(G)) for one n x n block (n <= 128); only the lower triangle of G is read; M upper triangle = 0
+__global__ void __launch_bounds__(IC_BASE)
+svd_invchol_base_kernel(const float* __restrict__ G, int64_t ldg, int n, float* __restrict__ M, int64_t ldm,
+                        uint32_t* __restrict__ fail) {
+  extern __shared__ float ic_smem[];
+  float (*Ls)[IC_BASE + 1] = reinterpret_cast<float (*)[IC_BASE + 1]>(ic_smem);
+  float (*Xs)[IC_BASE + 1] = reinterpret_cast<float (*)[IC_BASE + 1]>(ic_smem + IC_BASE * (IC_BASE + 1));
+  __shared__ float piv;
+  const int t = threadIdx.x;
+  for (int e = t; e < n * n; e += IC_BASE) {
+    const int i = e / n, k = e - i * n;
+    Ls[i][k] = (k <= i) ? G[(int64_t)i * ldg + k] : 0.f;
+  }
+  __syncthreads();
+  // left-looking Cholesky, thread t owns row t
+  for (int j = 0; j < n; ++j) {
+    float s = 0.f;
+    if (t >= j && t < n) {
+      for (int k = 0; k < j; ++k) s = fmaf(Ls[t][k], Ls[j][k], s);
+      s = Ls[t][j] - s;
+    }
+    if (t == j) {
+      const float d0 = Ls[j][j];
+      const float floor_ = (d0 > 0.f) ? 1e-7f * d0 : 1.f;
+      if (!(s > floor_)) { atomicOr(fail, 1u); s = floor_; }
+      piv = sqrtf(s);
+    }
+    __syncthreads();
+    if (t >= j && t < n) Ls[t][j] = (t == j) ? piv : s / piv;
+    __syncthreads();
+  }
+  // X = L^-1 by forward substitution, thread t owns column t
+  if (t < n) {
+    Xs[t][t] = 1.f / Ls[t][t];
+    for (int i = t + 1; i < n; ++i) {
+      float s = 0.f;
+      for (int k = t; k < i; ++k) s = fmaf(Ls[i][k], Xs[k][t], s);
+      Xs[i][t] = -s / Ls[i][i];
+    }
+  }
+  __syncthreads();
+  for (int e = t; e < n * n; e += IC_BASE) {
+    const int i = e / n, k = e - i * n;
+    M[(int64_t)i * ldm + k] = (k <= i) ? Xs[i][k] : 0.f;
+  }
+}
+
+// flag |= (max_ij |T_ij - delta_ij| > tol);  grid = rows of T
+__global__ void __launch_bounds__(256)
+svd_orth_defect_kernel(const float* __restrict__ T, int64_t ld, int r, float tol, uint32_t* __restrict__ fail) {
+  const int i = blockIdx.x;
+  float m = 0.f;
+  for (int j = threadIdx.x; j < r; j += blockDim.x) {
+    const float v = T[(int64_t)i * ld + j] - (i == j ? 1.f : 0.f);
+    m = fmaxf(m, (v == v) ? fabsf(v) : 1e30f);
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > tol) atomicOr(fail, 2u);
+}
+
+struct IcCtx {
+  void* stream;
+  void* gws;
+  size_t gws_bytes;
+  uint32_t* fail;
+};
+
+// M (n x n, zero-initialised by the caller) = inv(chol(G)); G is overwritten; scratch holds (2/3) n^2 floats
+static int invchol_rec(float* G, int64_t ldg, int n, float* M, int64_t ldm, float* scratch, const IcCtx& c) {
+  if (n <= IC_BASE) {
+    GRASP_LAUNCH(svd_invchol_base_kernel, dim3(1), dim3(IC_BASE), IC_SMEM, (cudaStream_t)c.stream, (const float*)G, ldg, n, M,
+                 ldm, c.fail);
+    return check_cuda(cudaGetLastError(), "svd_invchol_base_kernel");
+  }
+  const int h = ((n / 2 + 63) / 64) * 64, n2 = n - h;
+  int rc = invchol_rec(G, ldg, h, M, ldm, scratch, c);
+  if (rc) return rc;
+  float* T = scratch;
+  float* tmp = scratch + (size_t)n2 * h;
+  float* next = scratch + (size_t)2 * n2 * h;
+  float* G21 = G + (int64_t)h * ldg;
+  float* G22 = G21 + h;
+  float* M21 = M + (int64_t)h * ldm;
+  float* M22 = M21 + h;
+  const int P = GRASP_PREC_F16X3;
+  rc = tc_gemm_f32(0, 1, n2, h, h, 1.f, G21, ldg, M, ldm, 0.f, T, h, 0, P, c.gws, c.gws_bytes, c.stream);       // T = G21 M11^T
+  if (rc) return rc;
+  rc = tc_gemm_f32(0, 1, n2, n2, h, -1.f, T, h, T, h, 1.f, G22, ldg, 0, P, c.gws, c.gws_bytes, c.stream);      // G22 -= T T^T
+  if (rc) return rc;
+  rc = invchol_rec(G22, ldg, n2, M22, ldm, next, c);
+  if (rc) return rc;
+  rc = tc_gemm_f32(0, 0, n2, h, n2, 1.f, M22, ldm, T, h, 0.f, tmp, h, 0, P, c.gws, c.gws_bytes, c.stream);      // tmp = M22 T
+  if (rc) return rc;
+  return tc_gemm_f32(0, 0, n2, h, h, -1.f, tmp, h, M, ldm, 0.f, M21, ldm, 0, P, c.gws, c.gws_bytes, c.stream); // M21 = -tmp M11
+}
+
+// shared scratch of the preconditioning (one per call; the matrices are preconditioned one after another)
+struct PreShared {
+  float *G, *M, *scratch, *Q1;
+  void* gws;
+  size_t gws_bytes;
+};
+
+static size_t pre_gws_bytes(int64_t r, int64_t L) {
+  size_t a = tc_gemm_workspace_bytes(r, r, L, GRASP_PREC_F16X3);
+  size_t b = tc_gemm_workspace_bytes(r, L, r, GRASP_PREC_F16X3);
+  size_t c = tc_gemm_workspace_bytes(L, r, r, GRASP_PREC_F16X3);
+  if (b > a) a = b;
+  if (c > a) a = c;
+  return (a + 1023) / 1024 * 1024;
+}
+
+static size_t pre_shared_bytes(int64_t r, int64_t L) {
+  return (size_t)3 * r * r * 4 + (size_t)r * L * 4 + pre_gws_bytes(r, L) + 4 * 1024;
+}
+
+// Y0 = A (trans = 0, A is r x L) or A^T (trans = 1, A is L x r).  Writes Lm [r][r] and Q [r][L].
+static int svd_precondition(const float* A, int64_t lda, int trans, int r, int L, float* Lm, float* Q, uint32_t* fail,
+                            const PreShared& sh, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool attr = false;
+  if (!attr) {
+    int rc = check_cuda(cudaFuncSetAttribute(svd_invchol_base_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IC_SMEM),
+                        "svd_invchol attr");
+    if (rc) return rc;
+    attr = true;
+  }
+  const int P = GRASP_PREC_F16X3;
+  IcCtx c{stream, sh.gws, sh.gws_bytes, fail};
+  int rc = check_cuda(cudaMemsetAsync(fail, 0, 4, st), "svd pre memset");
+  if (rc) return rc;
+  const size_t rr = (size_t)r * r * 4;
+  // op(Y0) for the GEMM: Y0 as the left operand is (ta = trans, A); Y0 as op(B) = K x N is (tb = trans ? 1 : 0, A)
+  // G = Y0 Y0^T
+  rc = tc_gemm_f32(trans, trans ? 0 : 1, r, r, L, 1.f, A, lda, A, lda, 0.f, sh.G, r, 0, P, sh.gws, sh.gws_bytes, stream);
+  if (rc) return rc;
+  rc = check_cuda(cudaMemsetAsync(sh.M, 0, rr, st), "svd pre memset"); if (rc) return rc;
+  rc = invchol_rec(sh.G, r, r, sh.M, r, sh.scratch, c); if (rc) return rc;
+  // Q1 = M1 Y0
+  rc = tc_gemm_f32(0, trans ? 1 : 0, r, L, r, 1.f, sh.M, r, A, lda, 0.f, sh.Q1, L, 0, P, sh.gws, sh.gws_bytes, stream);
+  if (rc) return rc;
+  // second pass on Q1 (orthonormal to ~eps cond^2 after the first)
+  rc = tc_gemm_f32(0, 1, r, r, L, 1.f, sh.Q1, L, sh.Q1, L, 0.f, sh.G, r, 0, P, sh.gws, sh.gws_bytes, stream);
+  if (rc) return rc;
+  rc = check_cuda(cudaMemsetAsync(sh.M, 0, rr, st), "svd pre memset"); if (rc) return rc;
+  rc = invchol_rec(sh.G, r, r, sh.M, r, sh.scratch, c); if (rc) return rc;
+  rc = tc_gemm_f32(0, 0, r, L, r, 1.f, sh.M, r, sh.Q1, L, 0.f, Q, L, 0, P, sh.gws, sh.gws_bytes, stream);
+  if (rc) return rc;
+  // orthonormality of Q (also catches NaN / Inf from a failed factorisation)
+  rc = tc_gemm_f32(0, 1, r, r, L, 1.f, Q, L, Q, L, 0.f, sh.G, r, 0, P, sh.gws, sh.gws_bytes, stream);
+  if (rc) return rc;
+  GRASP_LAUNCH(svd_orth_defect_kernel, dim3((unsigned)r), dim3(256), 0, st, (const float*)sh.G, (int64_t)r, r, 1e-4f, fail);
+  // Lm = Y0 Q^T
+  rc = tc_gemm_f32(trans, 1, r, r, L, 1.f, A, lda, Q, L, 0.f, Lm, r, 0, P, sh.gws, sh.gws_bytes, stream);
+  if (rc) return rc;
+  return check_cuda(cudaGetLastError(), "svd precondition");
 }
 
 // ---------------------------------------------------------------------------
@@ -783,11 +965,17 @@ struct SvdPlan {
   int trans;           // 1 when m > n (work on A^T)
   int r, L, rp, Lp, ldz, p, npairs, nsplit, ntiles;
   size_t off_Z, off_G, off_ET, off_flag, off_stats, off_sigma, off_perm, off_Zp, off_ETp, off_T, off_gws, gws_bytes, bytes;
+  // CholeskyQR2-preconditioned matrix: the plan above is the one of the square r x r factor Lm (trans = 0) and
+  // these describe the original matrix
+  int pre;             // 1 when preconditioned
+  int trans0;          // original m > n
+  int64_t m0, n0, L0;  // original shape and its long side
+  size_t off_Lm, off_Q, off_prefail;
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static SvdPlan make_plan(int64_t m, int64_t n) {
+static SvdPlan make_plan_plain(int64_t m, int64_t n) {
   SvdPlan P{};
   P.m = m; P.n = n;
   P.trans = (m > n);
@@ -826,6 +1014,33 @@ static SvdPlan make_plan(int64_t m, int64_t n) {
   P.gws_bytes = align_up(g1 > g2 ? g1 : g2, 1024);
   P.off_gws = o;   o = align_up(o + P.gws_bytes, 1024);
   P.bytes = o;
+  P.pre = 0; P.trans0 = P.trans; P.m0 = m; P.n0 = n; P.L0 = P.L;
+  return P;
+}
+
+static bool pre_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GRASP_SVD_PRECOND"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
+
+// worth it when the rows shrink by a quarter or more (L + r -> 2 r) and the matrix is large enough for the
+// tensor-core phase to dominate
+static bool pre_eligible(int64_t m, int64_t n) {
+  const int64_t r = m < n ? m : n, L = m < n ? n : m;
+  return r >= 512 && 2 * L >= 3 * r;
+}
+
+static SvdPlan make_plan(int64_t m, int64_t n, bool allow_pre) {
+  if (!(allow_pre && pre_eligible(m, n))) return make_plan_plain(m, n);
+  const int64_t r = m < n ? m : n, L = m < n ? n : m;
+  SvdPlan P = make_plan_plain(r, r);
+  P.pre = 1; P.trans0 = (m > n); P.m0 = m; P.n0 = n; P.L0 = L;
+  size_t o = P.bytes;
+  P.off_Lm = o;      o = align_up(o + (size_t)r * r * 4, 1024);
+  P.off_Q = o;       o = align_up(o + (size_t)r * L * 4, 1024);
+  P.off_prefail = o; o = align_up(o + 256, 1024);
+  P.bytes = o;
   return P;
 }
 
@@ -835,12 +1050,19 @@ using namespace grasp;
 
 extern "C" size_t grasp_svd_workspace_bytes(int batch, const int64_t* m, const int64_t* n) {
   if (batch <= 0 || !m || !n) return 0;
-  size_t total = 0;
+  // sized for either route (the caller may switch the preconditioning off per call with GRASP_SVD_NO_PRECOND)
+  size_t total = 0, shared = 0;
   for (int i = 0; i < batch; ++i) {
     if (m[i] <= 0 || n[i] <= 0) return 0;
-    total += make_plan(m[i], n[i]).bytes;
+    const size_t a = make_plan(m[i], n[i], false).bytes, b = make_plan(m[i], n[i], true).bytes;
+    total += a > b ? a : b;
+    if (pre_eligible(m[i], n[i])) {
+      const int64_t r = m[i] < n[i] ? m[i] : n[i], L = m[i] < n[i] ? n[i] : m[i];
+      const size_t sb = pre_shared_bytes(r, L);
+      if (sb > shared) shared = sb;
+    }
   }
-  return total;
+  return total + shared + 1024;
 }
 
 extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t* m, const int64_t* n,
@@ -850,6 +1072,8 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
   if (batch < 0) return bad_arg("svd: batch");
   if (batch == 0) return 0;
   if (!A || !m || !n || !lda || !U || !S || !Vh || !ws) return bad_arg("svd: null");
+  const bool no_precond = (prec & GRASP_SVD_NO_PRECOND) != 0;
+  prec &= ~GRASP_SVD_NO_PRECOND;
   if (prec != GRASP_PREC_SIMT && prec != GRASP_PREC_BF16X3 && prec != GRASP_PREC_BF16X6 && prec != GRASP_PREC_F16X3)
     return bad_arg("svd: prec");
   if (max_sweeps <= 0) max_sweeps = 32;
@@ -914,19 +1138,53 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
   SvdPlan* plans = new SvdPlan[batch];
   unsigned char** base = new unsigned char*[batch];
   bool* done = new bool[batch];
+  const float** Aeff = new const float*[batch];     // what the Jacobi phase factors: A itself, or the square Lm
+  int64_t* ldaeff = new int64_t[batch];
+  const bool allow_pre = use_tc && pre_enabled() && !no_precond;
+  PreShared sh{};
+  int rc = 0;
   {
     unsigned char* cur = static_cast<unsigned char*>(ws);
+    int64_t rmax = 0, rlmax = 0;
+    size_t gmax = 0;
     for (int i = 0; i < batch; ++i) {
-      plans[i] = make_plan(m[i], n[i]);
+      plans[i] = make_plan(m[i], n[i], allow_pre);
       base[i] = cur;
       cur += plans[i].bytes;
       done[i] = false;
+      Aeff[i] = A[i];
+      ldaeff[i] = lda[i];
+      if (plans[i].pre) {
+        const int64_t r = plans[i].r, L = plans[i].L0;
+        if (r > rmax) rmax = r;
+        if (r * L > rlmax) rlmax = r * L;
+        const size_t gb = pre_gws_bytes(r, L);
+        if (gb > gmax) gmax = gb;
+      }
+    }
+    if (rmax > 0) {
+      cur = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(cur) + 1023) & ~(uintptr_t)1023);
+      sh.G = reinterpret_cast<float*>(cur);        cur += (size_t)rmax * rmax * 4;
+      sh.M = reinterpret_cast<float*>(cur);        cur += (size_t)rmax * rmax * 4;
+      sh.scratch = reinterpret_cast<float*>(cur);  cur += (size_t)rmax * rmax * 4;
+      sh.Q1 = reinterpret_cast<float*>(cur);       cur += (size_t)rlmax * 4;
+      cur = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(cur) + 1023) & ~(uintptr_t)1023);
+      sh.gws = cur; sh.gws_bytes = gmax;
+      for (int i = 0; i < batch && !rc; ++i) {
+        if (!plans[i].pre) continue;
+        float* Lm = reinterpret_cast<float*>(base[i] + plans[i].off_Lm);
+        rc = svd_precondition(A[i], lda[i], plans[i].trans0, plans[i].r, (int)plans[i].L0, Lm,
+                              reinterpret_cast<float*>(base[i] + plans[i].off_Q),
+                              reinterpret_cast<uint32_t*>(base[i] + plans[i].off_prefail), sh, stream);
+        Aeff[i] = Lm;
+        ldaeff[i] = plans[i].r;
+      }
     }
   }
-  int rc = 0;
   for (int i0 = 0; i0 < batch && !rc; ++i0) {
     if (done[i0]) continue;
-    // group up to J_MAXMAT matrices with the same working shape
+    // group up to J_MAXMAT matrices with the same working shape (a preconditioned wide matrix works on its
+    // square factor and shares launches with square matrices of the same order)
     SvdGroup g{};
     int members[J_MAXMAT];
     const SvdPlan& P = plans[i0];
@@ -952,7 +1210,7 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
       rc = check_cuda(cudaMemsetAsync(g.mat[j].stats, 0, J_STATS * 4, st), "svd memset");
       if (rc) break;
       dim3 grid((unsigned)(Q.ldz / 32), (unsigned)(Q.rp / 32));
-      GRASP_LAUNCH(svd_init_kernel, grid, dim3(32, 8), 0, st, A[i], lda[i], Q.r, Q.L, Q.trans,
+      GRASP_LAUNCH(svd_init_kernel, grid, dim3(32, 8), 0, st, Aeff[i], ldaeff[i], Q.r, Q.L, Q.trans,
                    g.mat[j].Z, Q.rp, Q.Lp, Q.ldz);
     }
     if (rc) break;
@@ -993,7 +1251,7 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
             GRASP_LAUNCH(jacobi_tc_kernel<JT_GRAM>, dim3(tc_grid_g), dim3(JT_THREADS), JtCfg<JT_GRAM>::SMEM_BYTES, st,
                          *maps, jp);
           } else {
-            GRASP_LAUNCH(svd_gram_kernel, dim3(g.nsplit, g.npairs, g.nmat), dim3(J_THREADS), 0, st, g, round);
+            GRASP_LAUNCH(svd_gram_kernel<float>, dim3(g.nsplit, g.npairs, g.nmat), dim3(J_THREADS), 0, st, g, round);
           }
           if (use_tc && !evd64_dbg && evd_warp)
             GRASP_LAUNCH(svd_evd_warp_kernel, dim3(g.npairs, g.nmat), dim3(EVW_THREADS), 0, st, g, round, sweep, tol,
@@ -1042,7 +1300,7 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
           rc = tc_gemm_f32(0, 0, Q.rp, Q.rp, Q.rp, -0.5f, T, Q.rp, QT, Q.ldz, 1.5f, QT, Q.ldz, 0, GRASP_PREC_BF16X6, gws,
                            Q.gws_bytes, stream);
           if (rc) break;
-          rc = tc_gemm_f32(0, Q.trans ? 1 : 0, Q.rp, Q.L, Q.r, 1.f, QT, Q.ldz, A[i], lda[i], 0.f, Zm, Q.ldz, 0,
+          rc = tc_gemm_f32(0, Q.trans ? 1 : 0, Q.rp, Q.L, Q.r, 1.f, QT, Q.ldz, Aeff[i], ldaeff[i], 0.f, Zm, Q.ldz, 0,
                            GRASP_PREC_BF16X6, gws, Q.gws_bytes, stream);
           if (!tc_cleanup) g.mat[j].ETp = nullptr;
           else GRASP_LAUNCH(jt_split_kernel, dim3((unsigned)ceil_div(n4, 256)), dim3(256), 0, st, Zm, Q.rp, Q.ldz,
@@ -1055,6 +1313,12 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
         // GRASP_SVD_TC_CLEANUP=1 runs them on the tensor cores (three-plane Gram) instead.
         const int extra = 3;
         const float cleanup_conv = 3e-6f;
+        // rotation threshold of the clean-up: with the exact (fp64-accumulated) Gram every pair above 1e-7 is
+        // rotated; with the fp32 Gram 1e-6 is its noise floor.  GRASP_SVD_CLEANUP_GRAM64=0 restores round 1.
+        bool cleanup_gram64 = true;
+        if (const char* e = getenv("GRASP_SVD_CLEANUP_GRAM64")) cleanup_gram64 = atoi(e) != 0;
+        float cleanup_tol = cleanup_gram64 ? 1e-7f : tol;
+        if (const char* e = getenv("GRASP_SVD_CLEANUP_TOL")) cleanup_tol = (float)atof(e);
         for (int s2 = 0; s2 < extra; ++s2) {
           const int sweep = max_sweeps + s2;
           for (int round = 0; round < g.p - 1; ++round) {
@@ -1062,11 +1326,13 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
               jp.round = round;
               GRASP_LAUNCH(jacobi_tc_kernel<JT_GRAM3>, dim3(tc_grid_g), dim3(JT_THREADS), JtCfg<JT_GRAM3>::SMEM_BYTES, st,
                            *maps, jp);
+            } else if (cleanup_gram64) {
+              GRASP_LAUNCH(svd_gram_kernel<double>, dim3(g.nsplit, g.npairs, g.nmat), dim3(J_THREADS), 0, st, g, round);
             } else {
-              GRASP_LAUNCH(svd_gram_kernel, dim3(g.nsplit, g.npairs, g.nmat), dim3(J_THREADS), 0, st, g, round);
+              GRASP_LAUNCH(svd_gram_kernel<float>, dim3(g.nsplit, g.npairs, g.nmat), dim3(J_THREADS), 0, st, g, round);
             }
             GRASP_LAUNCH(svd_evd_kernel<double>, dim3(g.npairs, g.nmat), dim3(EVD_THREADS), sizeof(EvdSmem<double>), st,
-                         g, round, sweep, tol, inner_cap);
+                         g, round, sweep, cleanup_tol, inner_cap);
             if (tc_cleanup) {
               GRASP_LAUNCH(jacobi_tc_kernel<JT_UPDATE>, dim3(tc_grid_u), dim3(JT_THREADS), JtCfg<JT_UPDATE>::SMEM_BYTES,
                            st, *maps, jp);
@@ -1117,7 +1383,31 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
       int64_t rr = Q.rp, kk = Q.rp;
       rc = grasp_topk_batched(1, &sc, &rr, &kk, &perm, stream);
       if (rc) break;
-      if (!Q.trans) {
+      if (Q.pre) {
+        // Lm = Usq S Wt (Wt = normalised rows of Y, Usq = QT^T) and Y0 = Lm Qb:  Y0 = Usq S (Wt Qb)
+        const int r = Q.r;
+        const int64_t L0 = Q.L0;
+        float* Wt = sh.G;                                             // [r][r], free since the preconditioning
+        const float* Qb = reinterpret_cast<const float*>(base[i] + Q.off_Q);
+        if (!Q.trans0) {
+          // A = Y0:  U = Usq,  Vh = Wt Qb
+          GRASP_LAUNCH(svd_emit_rows_kernel, dim3(r), dim3(256), 0, st, g.mat[j].Z, Q.ldz, 0, perm, sigma, 1, r, r, Wt,
+                       (int64_t)r, S[i]);
+          GRASP_LAUNCH(svd_emit_cols_kernel, dim3((r + 31) / 32, (unsigned)((r + 31) / 32)), dim3(32, 8), 0, st,
+                       g.mat[j].Z, Q.ldz, Q.Lp, perm, sigma, 0, r, r, U[i], (int64_t)r);
+          rc = tc_gemm_f32(0, 0, r, L0, r, 1.f, Wt, r, Qb, L0, 0.f, Vh[i], Q.n0, 0, GRASP_PREC_F16X3, sh.gws, sh.gws_bytes,
+                           stream);
+        } else {
+          // A = Y0^T = (Wt Qb)^T S Usq^T:  U = Qb^T Wt^T,  Vh = Usq^T = rows of QT
+          GRASP_LAUNCH(svd_emit_rows_kernel, dim3(r), dim3(256), 0, st, g.mat[j].Z, Q.ldz, 0, perm, sigma, 1, r, r, Wt,
+                       (int64_t)r, (float*)nullptr);
+          GRASP_LAUNCH(svd_emit_rows_kernel, dim3(r), dim3(256), 0, st, g.mat[j].Z, Q.ldz, Q.Lp, perm, sigma, 0, r, r,
+                       Vh[i], (int64_t)Q.n0, S[i]);
+          rc = tc_gemm_f32(1, 1, L0, r, r, 1.f, Qb, L0, Wt, r, 0.f, U[i], r, 0, GRASP_PREC_F16X3, sh.gws, sh.gws_bytes,
+                           stream);
+        }
+        if (rc) break;
+      } else if (!Q.trans) {
         // Vh = normalised rows of Y, U = QT^T
         GRASP_LAUNCH(svd_emit_rows_kernel, dim3(Q.r), dim3(256), 0, st, g.mat[j].Z, Q.ldz, 0, perm, sigma, 1, Q.r,
                      (int)Q.n, Vh[i], (int64_t)Q.n, S[i]);
@@ -1130,12 +1420,17 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
         GRASP_LAUNCH(svd_emit_rows_kernel, dim3(Q.r), dim3(256), 0, st, g.mat[j].Z, Q.ldz, Q.Lp, perm, sigma, 0, Q.r,
                      (int)Q.n, Vh[i], (int64_t)Q.n, S[i]);
       }
-      if (info) GRASP_LAUNCH(svd_info_kernel, dim3(1), dim3(1), 0, st, g.mat[j].stats, info + 4 * i);
+      if (info)
+        GRASP_LAUNCH(svd_info_kernel, dim3(1), dim3(1), 0, st, g.mat[j].stats,
+                     Q.pre ? reinterpret_cast<const uint32_t*>(base[i] + Q.off_prefail) : (const uint32_t*)nullptr,
+                     info + 4 * i);
       rc = check_cuda(cudaGetLastError(), "svd finalize");
     }
   }
   delete[] plans;
   delete[] base;
   delete[] done;
+  delete[] Aeff;
+  delete[] ldaeff;
   return rc;
 }

@@ -112,18 +112,23 @@ def _batched_svd_local(weights: Sequence[torch.Tensor], max_group: int = 8):
             infos.append((chunk, info))
             for i, usv in zip(chunk, usvs):
                 out[i] = usv
-    # one synchronisation for the whole call: a Jacobi run that hit its sweep limit would hand non-orthogonal
-    # factors to scoring and compile, so it is retried with the pure-fp32 path and refused if that fails too
+    # one synchronisation for the whole call: a Jacobi run that hit its sweep limit, or a CholeskyQR2
+    # preconditioning that was not sound (cond^2 beyond fp32: ill-conditioned trained weights), would hand
+    # non-orthogonal factors to scoring and compile.  Such a matrix is factored again as it is (no preconditioning),
+    # then on the pure-fp32 path, and refused if that fails too.
     flags = torch.cat([info[:, 1] for _, info in infos]).cpu().tolist() if infos else []
     order = [i for chunk, _ in infos for i in chunk]
     for i, ok in zip(order, flags):
         if ok:
             continue
-        logger.warning("SVD of matrix %d %s did not converge; retrying on the fp32 CUDA-core path", i,
-                       tuple(weights[i].shape))
-        usvs, info = ops.svd_batched([weights[i]], prec=ops.PREC_SIMT, max_sweeps=48, return_info=True)
+        shape = tuple(weights[i].shape)
+        logger.warning("SVD of matrix %d %s: preconditioning unsound or sweep limit hit; factoring it as it is", i, shape)
+        usvs, info = ops.svd_batched([weights[i]], return_info=True, precondition=False)
         if not int(info[0, 1].item()):
-            raise SvdNotConverged(f"SVD of a {tuple(weights[i].shape)} matrix did not converge")
+            logger.warning("SVD of matrix %d %s did not converge; retrying on the fp32 CUDA-core path", i, shape)
+            usvs, info = ops.svd_batched([weights[i]], prec=ops.PREC_SIMT, max_sweeps=48, return_info=True)
+            if not int(info[0, 1].item()):
+                raise SvdNotConverged(f"SVD of a {shape} matrix did not converge")
         out[i] = usvs[0]
     return out
 

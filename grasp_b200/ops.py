@@ -171,8 +171,9 @@ def bi_chain(hiddens: Sequence[torch.Tensor], acc: torch.Tensor, scale: float = 
 
 # -------------------------------------------------------------------------- SVD
 def svd_batched(mats: Sequence[torch.Tensor], prec: Optional[int] = None, max_sweeps: int = 0,
-                return_info: bool = False):
-    """Thin SVD of each fp32 matrix: returns [(U [m,r], S [r] descending, Vh [r,n])]."""
+                return_info: bool = False, precondition: bool = True):
+    """Thin SVD of each fp32 matrix: returns [(U [m,r], S [r] descending, Vh [r,n])].
+    precondition=False factors wide / tall matrices as they are (no CholeskyQR2 reduction to a square factor)."""
     lib = _lib.load()
     dev = _need_cuda(*mats)
     if len(mats) == 0:
@@ -199,8 +200,8 @@ def svd_batched(mats: Sequence[torch.Tensor], prec: Optional[int] = None, max_sw
         check(lib.grasp_svd_batched(len(As), _lib.ptr_array([a.data_ptr() for a in As]), m_a, n_a, _lib.i64_array(n),
                                     _lib.ptr_array([u.data_ptr() for u in Us]),
                                     _lib.ptr_array([s.data_ptr() for s in Ss]),
-                                    _lib.ptr_array([v.data_ptr() for v in Vs]), info.data_ptr(), _prec(prec),
-                                    int(max_sweeps), ws.data_ptr(), ws.numel(), _stream()), "grasp_svd_batched")
+                                    _lib.ptr_array([v.data_ptr() for v in Vs]), info.data_ptr(),
+                                    _prec(prec) | (0 if precondition else _lib.SVD_NO_PRECOND), int(max_sweeps), ws.data_ptr(), ws.numel(), _stream()), "grasp_svd_batched")
         timers.stop("grasp_svd_batched", t0,
                     flops=sum(8.0 * max(a, b) * min(a, b) ** 2 + 4.0 / 3.0 * min(a, b) ** 3 for a, b in zip(m, n)),
                     mma_per_flop=0.0)

@@ -48,6 +48,9 @@ extern "C" {
 #define GRASP_PREC_BF16X3 3
 #define GRASP_PREC_BF16X6 6
 #define GRASP_PREC_F16X3  16
+/* flag, OR-ed into the `prec` of grasp_svd_batched: factor the matrix as it is, without the CholeskyQR2
+ * preconditioning of wide / tall matrices (the retry when info reports a failed preconditioning) */
+#define GRASP_SVD_NO_PRECOND 0x100
 
 int         grasp_abi_version(void);
 const char* grasp_last_error(void);
@@ -81,7 +84,9 @@ int grasp_bi_chain(const void* const* hiddens, int n_states, int64_t rows, int64
  * (a3) thin SVD, replaces torch.linalg.svd(w, full_matrices=False) at
  * modeling_grasp.py:231.  A[i] is m[i] x n[i] fp32 (lda[i]); outputs
  * U[i] [m, r] (ld r), S[i] [r] descending, Vh[i] [r, n] (ld n), r = min(m,n).
- * info (device int32 [4*batch]): {sweeps used, converged(0/1),
+ * Wide / tall matrices (long side >= 1.5 x short side, short side >= 512) are first reduced to the square factor
+ * of a CholeskyQR2 (tensor-core GEMMs), unless GRASP_SVD_NO_PRECOND is set in `prec`.
+ * info (device int32 [4*batch]): {sweeps used, converged(0/1; 0 also when the preconditioning was not sound),
  * float bits of the last sweep's max relative off-diagonal, sweeps of the
  * tensor-core phase}.
  * prec: GRASP_PREC_*; max_sweeps <= 0 selects the default (32).

@@ -13,7 +13,10 @@ def rel(a, b):
 
 
 # ------------------------------------------------------------------------- prepared operands
-@pytest.mark.parametrize("M,N,K", [(300, 204, 1000), (1024, 4096, 4096), (511, 11008, 4096), (129, 72, 20), (64, 8, 8)])
+@pytest.mark.parametrize("M,N,K", [(300, 204, 1000), (1024, 4096, 4096), (511, 11008, 4096), (129, 72, 20), (64, 8, 8),
+                                   (2300, 520, 298),      # short K (two K blocks per TMEM drain), ragged M and N tiles
+                                   (2300, 298, 1028),     # N % 4 != 0: the direct (unstaged) epilogue
+                                   (2049, 4096, 4096)])   # more M blocks than one super-row of the tile order
 def test_gemm_planes_forward_and_backward_forms(cuda, M, N, K):
     from grasp_b200 import _lib, ops
     g = torch.Generator().manual_seed(M + N + K)

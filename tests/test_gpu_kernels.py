@@ -141,6 +141,42 @@ def test_svd_random_weights(cuda, m, n):
     check_svd(A, U, S, Vh, restate.svd(A)[1])
 
 
+@pytest.mark.parametrize("m,n", [(768, 2304), (2304, 768), (520, 1500), (1030, 520)])
+def test_svd_preconditioned_wide_and_tall(cuda, m, n):
+    """Wide / tall matrices go through the CholeskyQR2 reduction to a square factor; the factors must be as good as
+    those of the direct route (precondition=False) and both must match the oracle."""
+    from grasp_b200 import ops
+    g = torch.Generator().manual_seed(m * 3 + n)
+    A = torch.randn(m, n, generator=g) * 0.02
+    S_ref = restate.svd(A)[1]
+    outs, info = ops.svd_batched([A.to(cuda), A.to(cuda)], return_info=True)           # two of a kind: one launch group
+    assert torch.all(info.cpu()[:, 1] == 1), info
+    for U, S, Vh in outs:
+        check_svd(A, U, S, Vh, S_ref)
+    (U2, S2, Vh2), = ops.svd_batched([A.to(cuda)], precondition=False)
+    check_svd(A, U2, S2, Vh2, S_ref)
+    assert ((outs[0][1] - S2).abs().max() / S2[0]).item() < 2e-6
+
+
+def test_svd_preconditioning_flags_ill_conditioned_input_and_the_engine_recovers(cuda):
+    """cond(A) = 1e6: cond(A A^T) is beyond fp32, the Cholesky factorisation breaks down.  The call reports it in
+    info[1] (never silently wrong factors) and engine.batched_svd factors the matrix again without preconditioning."""
+    from grasp_b200 import engine, ops
+    g = torch.Generator().manual_seed(5)
+    r, L = 512, 1536
+    Uo, _ = torch.linalg.qr(torch.randn(r, r, generator=g, dtype=torch.float64))
+    Vo, _ = torch.linalg.qr(torch.randn(L, r, generator=g, dtype=torch.float64))
+    sv = torch.logspace(0, -6, r, dtype=torch.float64)
+    A = ((Uo * sv) @ Vo.T).float()
+    _, info = ops.svd_batched([A.to(cuda)], return_info=True)
+    assert int(info.cpu()[0, 1]) == 0, "an unsound preconditioning must be reported"
+    (U, S, Vh), = engine.batched_svd([A.to(cuda)])
+    A64, S64 = A.double(), torch.linalg.svdvals(A.double())
+    assert ((S.double().cpu() - S64).abs().max() / S64[0]).item() < 1e-5
+    rec = (torch.linalg.norm((U.double().cpu() * S.double().cpu()) @ Vh.double().cpu() - A64) / torch.linalg.norm(A64)).item()
+    assert rec < 1e-5, rec
+
+
 def test_svd_batched_mixed_shapes_and_info(cuda):
     from grasp_b200 import ops
     g = torch.Generator().manual_seed(11)
