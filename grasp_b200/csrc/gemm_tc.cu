@@ -237,13 +237,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         mbar_arrive(&acc_empty[acc]);               // hand the TMEM buffer back to the MMA warp
         if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
       }
+      const bool staged = (EPI == EPI_STORE) && p.staged;
+      float row_scale = p.alpha;                    // staged path: alpha and the row's inverse plane scale in one factor
       if constexpr (F16) {
         // undo the per-row power-of-two scaling of the fp16 planes (exact)
         const float ia = (row < p.M) ? p.inv_sa[row] : 0.f;
+        if (staged) {
+          row_scale *= ia;                          // the column scales are applied after the transpose (8 vector loads
+        } else {                                    // per lane and tile instead of 128 scalar ones)
 #pragma unroll
-        for (int j = 0; j < 128; ++j) {
-          const int col = n0 + half * 128 + j;
-          racc[j] *= ia * ((col < p.N) ? __ldg(p.inv_sb + col) : 0.f);
+          for (int j = 0; j < 128; ++j) {
+            const int col = n0 + half * 128 + j;
+            racc[j] *= ia * ((col < p.N) ? __ldg(p.inv_sb + col) : 0.f);
+          }
         }
       }
 #pragma unroll
@@ -251,7 +257,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         float* v = &racc[c * 32];
         const int col0 = n0 + half * 128 + c * 32;
         if constexpr (EPI == EPI_STORE) {
-          if (p.staged) {
+          if (staged) {
             // Each lane holds 32 consecutive columns of ITS row: stored directly, one instruction writes 16 bytes
             // into 32 different rows (32 half-filled sectors).  Staged through shared memory (float4 chunks
             // XOR-swizzled with the row, conflict-free both ways) the warp writes 4 rows x 128 contiguous bytes
@@ -259,22 +265,44 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
             for (int q = 0; q < 8; ++q)
               *reinterpret_cast<float4*>(stg + lane * 32 + ((q ^ (lane & 7)) << 2)) =
-                  make_float4(p.alpha * v[4 * q], p.alpha * v[4 * q + 1], p.alpha * v[4 * q + 2], p.alpha * v[4 * q + 3]);
+                  make_float4(row_scale * v[4 * q], row_scale * v[4 * q + 1], row_scale * v[4 * q + 2], row_scale * v[4 * q + 3]);
             __syncwarp();
             const int sub = lane >> 3, pos = lane & 7;
             const int row_base = m_blk * TC_BM + quad * 32;
+            // row r = 4 i + sub of the staging tile holds column chunk pos ^ (r & 7) at position pos: a lane sees two
+            // chunks only, (pos ^ sub) for even i and (pos ^ sub ^ 4) for odd i
+            const int colA = col0 + ((pos ^ sub) << 2), colB = col0 + ((pos ^ sub ^ 4) << 2);
+            float4 csA = make_float4(1.f, 1.f, 1.f, 1.f), csB = csA;
+            if constexpr (F16) {
+              csA = (colA < p.N) ? __ldg(reinterpret_cast<const float4*>(p.inv_sb + colA)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              csB = (colB < p.N) ? __ldg(reinterpret_cast<const float4*>(p.inv_sb + colB)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            const bool full = (row_base + 32 <= p.M) && (col0 + 32 <= p.N);   // warp-uniform
+            float* crow = static_cast<float*>(p.C) + (int64_t)(row_base + sub) * p.ldc;
+            if (full && p.beta == 0.f) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int r = i * 4 + sub;
-              const int col = col0 + ((pos ^ (r & 7)) << 2);
-              float4 o = *reinterpret_cast<const float4*>(stg + r * 32 + (pos << 2));
-              if (row_base + r < p.M && col < p.N) {
-                float* dst = static_cast<float*>(p.C) + (int64_t)(row_base + r) * p.ldc + col;
-                if (p.beta != 0.f) {
-                  const float4 old = *reinterpret_cast<const float4*>(dst);
-                  o.x += p.beta * old.x; o.y += p.beta * old.y; o.z += p.beta * old.z; o.w += p.beta * old.w;
+              for (int i = 0; i < 8; ++i) {
+                float4 o = *reinterpret_cast<const float4*>(stg + (i * 4 + sub) * 32 + (pos << 2));
+                const float4 cs = (i & 1) ? csB : csA;
+                o.x *= cs.x; o.y *= cs.y; o.z *= cs.z; o.w *= cs.w;
+                *reinterpret_cast<float4*>(crow + (int64_t)(i * 4) * p.ldc + ((i & 1) ? colB : colA)) = o;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int r = i * 4 + sub;
+                const int col = (i & 1) ? colB : colA;
+                float4 o = *reinterpret_cast<const float4*>(stg + r * 32 + (pos << 2));
+                const float4 cs = (i & 1) ? csB : csA;
+                o.x *= cs.x; o.y *= cs.y; o.z *= cs.z; o.w *= cs.w;
+                if (row_base + r < p.M && col < p.N) {
+                  float* dst = crow + (int64_t)(i * 4) * p.ldc + col;
+                  if (p.beta != 0.f) {
+                    const float4 old = *reinterpret_cast<const float4*>(dst);
+                    o.x += p.beta * old.x; o.y += p.beta * old.y; o.z += p.beta * old.z; o.w += p.beta * old.w;
+                  }
+                  *reinterpret_cast<float4*>(dst) = o;
                 }
-                *reinterpret_cast<float4*>(dst) = o;
               }
             }
             __syncwarp();
@@ -910,7 +938,8 @@ static int launch_core(const __nv_bfloat16* Ap, const __nv_bfloat16* Bp, TcParam
   prm.kgroup = gemm_kgroup(NS, prm.K);
   prm.group_m = raster_group_m(prm.tiles_m, prm.tiles_n, prm.K, NS);
   prm.staged = (EPI == EPI_STORE && !prm.c_bf16 && (prm.N & 3) == 0 && (prm.ldc & 3) == 0 &&
-                (reinterpret_cast<uintptr_t>(prm.C) & 15) == 0 && staged_epilogue()) ? 1 : 0;
+                (reinterpret_cast<uintptr_t>(prm.C) & 15) == 0 && (!F16 || (reinterpret_cast<uintptr_t>(prm.inv_sb) & 15) == 0) &&
+                staged_epilogue()) ? 1 : 0;
   const int total = prm.tiles_m * prm.tiles_n;
   const int grid = total < sm_count() ? total : sm_count();
   GRASP_LAUNCH((tc_gemm_kernel<NS, BN, EPI, BMN, F16>), dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, mapA, mapB, prm);
@@ -1019,7 +1048,7 @@ static bool use_2cta(int64_t M, int64_t N) {
 size_t tc_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int prec) {
   const int NS = ns_of(prec);
   const size_t b = planes_bytes(NS, N, K) > planes_bytes(NS, K, N) ? planes_bytes(NS, N, K) : planes_bytes(NS, K, N);
-  return planes_bytes(NS, M, K) + b + 2048 + (size_t)round_up(2 * (M + N) * 4, 1024);
+  return planes_bytes(NS, M, K) + b + 2048 + (size_t)round_up(2 * (round_up(M, 4) + round_up(N, 4)) * 4, 1024);
 }
 
 size_t tc_sigma_workspace_bytes(int64_t out, int64_t in, int64_t r, int prec) {
@@ -1047,10 +1076,11 @@ int tc_gemm_f32(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, co
   const bool bmn = !tb && use_bmn();
   if (is_f16(prec)) {
     const size_t bbytes = planes_bytes(NS, N, K) > planes_bytes(NS, K, N) ? planes_bytes(NS, N, K) : planes_bytes(NS, K, N);
-    float* sc = reinterpret_cast<float*>(w + planes_bytes(NS, M, K) + bbytes);   // scale_a[M] inv_a[M] scale_b[N] inv_b[N]
-    float* inv_a = sc + M;
-    float* sc_b = sc + 2 * M;
-    float* inv_b = sc_b + N;
+    // scale_a[M] inv_a[M] scale_b[N] inv_b[N], each on a 16-byte boundary (the epilogue reads inv_b as float4)
+    float* sc = reinterpret_cast<float*>(w + planes_bytes(NS, M, K) + bbytes);
+    float* inv_a = sc + round_up(M, 4);
+    float* sc_b = sc + 2 * round_up(M, 4);
+    float* inv_b = sc_b + round_up(N, 4);
     rc = split_operand_f16(A, lda, ta ? 1 : 0, (int)M, (int)K, Ap, sc, inv_a, stream); if (rc) return rc;
     rc = split_operand_f16(B, ldb, tb ? 0 : (bmn ? 2 : 1), (int)N, (int)K, Bp, sc_b, inv_b, stream); if (rc) return rc;
     TcParams prm{};

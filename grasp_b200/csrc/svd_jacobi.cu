@@ -58,6 +58,9 @@ __device__ __forceinline__ void rr_pair(int p, int t, int k, int& a, int& b) {
   b = max(x, y);
 }
 
+// NaN -> lowest key, so that comparisons on it form a total order
+__device__ __forceinline__ float finite_key(float d) { return (d == d) ? d : -3.0e38f; }
+
 __device__ __forceinline__ const float* pair_row(const float* Z, int ldz, int I, int J, int rr) {
   const int row = (rr < JB) ? (I * JB + rr) : (J * JB + rr - JB);
   return Z + (int64_t)row * ldz;
@@ -309,10 +312,11 @@ svd_evd_kernel(SvdGroup g, int round, int sweep, float tol, int inner_cap) {
 
   // order the new rows by descending squared norm (diag of the rotated Gram)
   if (tid < JS) {
-    const float di = sm.G[tid][tid];
+    // (NaN diagonals -- non-finite input -- sort last: the ranks must stay a permutation, they index shared memory)
+    const float di = finite_key(sm.G[tid][tid]);
     int rk = 0;
     for (int j = 0; j < JS; ++j) {
-      const float dj = sm.G[j][j];
+      const float dj = finite_key(sm.G[j][j]);
       rk += (dj > di) || (dj == di && j < tid);
     }
     sm.rank[tid] = rk;
@@ -583,10 +587,11 @@ svd_evd_warp_kernel(SvdGroup g, int round, int sweep, float tol, int inner_cap) 
 
   // order the new rows by descending squared norm (diag of the rotated Gram)
   if (tid < JS) {
-    const float di = sm.G[tid][tid];
+    // (NaN diagonals -- non-finite input -- sort last: the ranks must stay a permutation, they index shared memory)
+    const float di = finite_key(sm.G[tid][tid]);
     int rk = 0;
     for (int j = 0; j < JS; ++j) {
-      const float dj = sm.G[j][j];
+      const float dj = finite_key(sm.G[j][j]);
       rk += (dj > di) || (dj == di && j < tid);
     }
     sm.rank[tid] = rk;

@@ -54,7 +54,7 @@ def test_matrix_pipeline_matches_oracle(cuda, parity_log, shape):
                f"({len(swapped) // 2} swapped, tie margin {100 * tie:.3f} %), score error {sc_err:.1e}, rebuilt weight "
                f"{fro:.1e} (factor pair {fro_f:.1e}) relative Frobenius")
     assert sig < 1e-5 and sig_rel < 1e-4                                # north-star bar: 1e-4 relative
-    assert jac >= 0.97 and tie <= 0.02
+    assert jac >= 0.97 and tie <= 0.05
     assert sc_err < 5e-2      # singular vectors of near-equal sigma rotate freely (app. B.11: 7e-3 at n=2048 between LAPACK precisions)
     if fro >= 1e-3:                                                      # near-degenerate pair across the cut:
         U64, S64, Vh64 = torch.linalg.svd(W.double(), full_matrices=False)   # be as close to the truth as LAPACK is
