@@ -19,7 +19,7 @@ INCLUDE = ROOT.parent / "include"
 BUILD = ROOT / "_build"
 LIB = ROOT / "libgrasp_b200.so"
 
-SOURCES = ["abi.cu", "bi.cu", "topk.cu", "svd_jacobi.cu", "score.cu", "rebuild.cu", "gemm_tc.cu", "layer_ops.cu"]
+SOURCES = ["abi.cu", "bi.cu", "topk.cu", "svd_jacobi.cu", "score.cu", "rebuild.cu", "gemm_tc.cu", "layer_ops.cu", "attention.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -834,6 +834,11 @@ static int make_plane_map(CUtensorMap* map, const void* planes, int NS, int R, i
   return 0;
 }
 
+// the same for other translation units (attention.cu)
+int tc_make_plane_map(CUtensorMap* map, const void* planes, int NS, int R, int K, int Kp, int box_rows, int box_inner) {
+  return make_plane_map(map, planes, NS, R, K, Kp, box_rows, box_inner);
+}
+
 // generic bf16 3-D map used by the SVD tensor-core kernels (declared in tc_common.cuh)
 int tc_make_map_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                    uint64_t stride2_bytes, uint32_t box0, uint32_t box1) {

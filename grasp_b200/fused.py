@@ -16,7 +16,8 @@ an explicit forward and an explicit backward:
   * the backward stops where no GRASPLayer below needs a gradient (autograd prunes the same
     way), and GRASPLayers harvest G += dY^T X exactly as engine.SigmaLinearFn does.
 
-Attention stays torch's scaled_dot_product_attention (library code) behind `sdpa_fwd/bwd`.
+Attention is grasp_attn_fwd / grasp_attn_bwd (tcgen05 flash kernels on the same fp16-plane arithmetic) for
+head dimensions 64 and 128, torch's scaled_dot_product_attention otherwise, behind `sdpa_fwd/bwd`.
 All arithmetic sits behind a small backend object so that the orchestration (which tensors
 are saved, every backward formula) is testable on CPU against autograd with a torch backend
 that lives in tests/ -- the product backend below has no CPU path.
@@ -140,7 +141,16 @@ def _sdpa(q, k, v, B, S, H, Hkv, D, scale):
     return o.transpose(1, 2).reshape(B * S, H * D)
 
 
+def _own_attention(q, D) -> bool:
+    """The library's tensor-core attention applies (fp32 CUDA activations, head_dim 64 / 128); otherwise torch's
+    scaled_dot_product_attention (library code) serves, e.g. for the 16 / 32-wide heads of the test models."""
+    return q.is_cuda and q.dtype == torch.float32 and ops.attn_supported(D)
+
+
 def sdpa_fwd(q, k, v, B, S, H, Hkv, D, scale, keep):
+    if _own_attention(q, D):
+        out, ctx = ops.attn_fwd(q, k, v, B, S, H, Hkv, D, scale)
+        return out, (("grasp", ctx) if keep else None)
     if not keep:
         return _sdpa(q, k, v, B, S, H, Hkv, D, scale), None
     ql, kl, vl = (t.detach().requires_grad_(True) for t in (q, k, v))
@@ -150,6 +160,8 @@ def sdpa_fwd(q, k, v, B, S, H, Hkv, D, scale, keep):
 
 
 def sdpa_bwd(ctx, d_out):
+    if ctx[0] == "grasp":
+        return ops.attn_bwd(ctx[1], d_out)
     out, ql, kl, vl = ctx
     dq, dk, dv = torch.autograd.grad(out, (ql, kl, vl), d_out)
     return dq.contiguous(), dk.contiguous(), dv.contiguous()

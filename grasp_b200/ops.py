@@ -598,3 +598,52 @@ def ce_loss_bwd_(logits: torch.Tensor, labels: torch.Tensor, coef: torch.Tensor)
                                     _stream()), "grasp_ce_loss_bwd")
         timers.stop("grasp_rowops", t0, bytes_=8.0 * rows * V)
     return loss
+
+
+# ----------------------------------------------------------------------- attention
+ATTN_HEAD_DIMS = (64, 128)
+
+
+def attn_supported(head_dim: int) -> bool:
+    return int(head_dim) in ATTN_HEAD_DIMS
+
+
+def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, S: int, H: int, Hkv: int, D: int, scale: float):
+    """Causal attention of [B*S, H*D] / [B*S, Hkv*D] activations (after RoPE).  Returns (out [B*S, H*D], ctx);
+    ctx carries what attn_bwd needs (operand planes of q, k, v, the output and the row log-sum-exps)."""
+    lib = _lib.load()
+    dev = _need_cuda(q, k, v)
+    if q.shape != (B * S, H * D) or k.shape != (B * S, Hkv * D) or v.shape != k.shape:
+        raise ValueError("attn_fwd: q [B*S, H*D], k / v [B*S, Hkv*D] expected")
+    qo, ko, vo = (split_f16(t, _lib.SCALE_TENSOR) for t in (q, k, v))
+    out = torch.empty(B * S, H * D, dtype=torch.float32, device=dev)
+    lse2 = torch.empty(B * H * S, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        t0 = timers.start()
+        check(lib.grasp_attn_fwd(qo.planes, qo.inv.data_ptr(), ko.planes, ko.inv.data_ptr(), vo.planes, vo.inv.data_ptr(),
+                                 B, S, H, Hkv, D, float(scale), out.data_ptr(), lse2.data_ptr(), _stream()), "grasp_attn_fwd")
+        timers.stop("grasp_attn", t0, flops=2.0 * B * H * S * S * D, mma_per_flop=3.0)      # causal: half of 4 S^2 D
+    return out, (qo, ko, vo, out, lse2, (B, S, H, Hkv, D, float(scale)))
+
+
+def attn_bwd(ctx, d_out: torch.Tensor):
+    """(dq [B*S, H*D], dk, dv [B*S, Hkv*D]) for the ctx of attn_fwd and dL/d(out)."""
+    lib = _lib.load()
+    qo, ko, vo, out, lse2, (B, S, H, Hkv, D, scale) = ctx
+    dev = _need_cuda(d_out)
+    d_out = _f32c(d_out, "d_out")
+    if d_out.shape != (B * S, H * D):
+        raise ValueError("attn_bwd: d_out must be [B*S, H*D]")
+    doo = split_f16(d_out, _lib.SCALE_TENSOR)
+    dq = torch.empty(B * S, H * D, dtype=torch.float32, device=dev)
+    dk = torch.empty(B * S, Hkv * D, dtype=torch.float32, device=dev)
+    dv = torch.empty(B * S, Hkv * D, dtype=torch.float32, device=dev)
+    delta = torch.empty(B * H * S, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        t0 = timers.start()
+        check(lib.grasp_attn_bwd(qo.planes, qo.inv.data_ptr(), ko.planes, ko.inv.data_ptr(), vo.planes, vo.inv.data_ptr(),
+                                 doo.planes, doo.inv.data_ptr(), d_out.data_ptr(), out.data_ptr(), lse2.data_ptr(), B, S, H, Hkv,
+                                 D, scale, dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), delta.data_ptr(), _stream()),
+              "grasp_attn_bwd")
+        timers.stop("grasp_attn", t0, flops=7.0 * B * H * S * S * D, mma_per_flop=3.0)      # 7 products, causal half
+    return dq, dk, dv

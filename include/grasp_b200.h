@@ -166,7 +166,7 @@ int    grasp_gemm_f32(int ta, int tb, int64_t M, int64_t N, int64_t K, float alp
  * weight by every micro-batch, forward as [N][K] and backward as [K][N], and one
  * activation by several weights; the split pre-pass is therefore callable on
  * its own and its result reusable:
- *   planes  [2][rows][round8(cols)] fp16 (hi, lo) of src * scale, in the STORED
+ *   planes  [2][rows][pitch(cols)] fp16 (hi, lo) of src * scale, in the STORED
  *           orientation, grasp_gemm_planes_bytes() bytes, 1024-byte aligned
  *   inv     inverse scales: GRASP_SCALE_ROWS   -> [rows], one power of two per row
  *                           GRASP_SCALE_TENSOR -> [max(rows,cols) + 1] floats, one
@@ -221,6 +221,24 @@ int grasp_swiglu_bwd(const float* dh, const float* g, const float* u, int64_t ro
                      void* du_planes, float* du_inv, void* stream);
 int grasp_ce_loss_bwd(float* logits, const int64_t* labels, const float* coef, int64_t rows, int64_t V,
                       float* loss, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * (f1) causal self-attention of the calibration passes (the reference reaches it through
+ * transformers' LlamaAttention inside self.model(...) / loss.backward(), modeling_grasp.py:347-354):
+ *   O = softmax(scale * Q K^T + causal mask) V  per (batch, head), grouped-query heads (H % Hkv == 0),
+ * in the F16X3 tensor-core arithmetic.  q / k / v / dO are given as prepared operands of the
+ * [B*S, heads*D] activations (after RoPE), split with GRASP_SCALE_TENSOR; head_dim D is 64 or 128.
+ *   fwd: out [B*S][H*D] fp32, lse2 [B][H][S] = log2 sum_k exp(scale * q.k) (kept for the backward)
+ *   bwd: dq [B*S][H*D], dk / dv [B*S][Hkv*D] (summed over the query heads of a group), from dO (fp32 and its
+ *        planes), the forward's out and lse2; delta_ws holds B*H*S floats.
+ * ------------------------------------------------------------------------- */
+int grasp_attn_fwd(const void* q_planes, const float* inv_q, const void* k_planes, const float* inv_k,
+                   const void* v_planes, const float* inv_v, int B, int S, int H, int Hkv, int D, float scale,
+                   float* out, float* lse2, void* stream);
+int grasp_attn_bwd(const void* q_planes, const float* inv_q, const void* k_planes, const float* inv_k,
+                   const void* v_planes, const float* inv_v, const void* do_planes, const float* inv_do,
+                   const float* dO, const float* O, const float* lse2, int B, int S, int H, int Hkv, int D,
+                   float scale, float* dq, float* dk, float* dv, float* delta_ws, void* stream);
 
 #ifdef __cplusplus
 }
