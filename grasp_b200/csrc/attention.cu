@@ -32,6 +32,41 @@ constexpr int AT_THREADS = 192;
 constexpr float AT_P_SCALE = 16384.f;          // probabilities (<= 1) as fp16 planes: p * 2^14 = hi + lo
 constexpr float AT_P_INV = 1.f / 16384.f;
 
+// 2^x on the SFU (rel. error ~2^-22, -inf -> 0)
+__device__ __forceinline__ float at_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// 8 fp32 values -> 8 fp16 hi and 8 fp16 lo (x = hi + lo), packed in element order (two conversions per pair)
+__device__ __forceinline__ void at_split8(const float* v, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __half2 h2 = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+    const float2 f = __half22float2(h2);
+    const __half2 l2 = __floats2half2_rn(v[2 * e] - f.x, v[2 * e + 1] - f.y);
+    h[e] = *reinterpret_cast<const uint32_t*>(&h2);
+    l[e] = *reinterpret_cast<const uint32_t*>(&l2);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// 64 fp32 values of this thread's row -> (hi, lo) fp16 planes of a [128][64] K-major tile with the 128-byte
+// swizzle (16-byte chunk c8 of row r sits at c8 ^ (r & 7))
+__device__ __forceinline__ void at_store_planes(unsigned char* T, int plane_bytes, int row, const float* v) {
+#pragma unroll
+  for (int c8 = 0; c8 < 8; ++c8) {
+    uint4 hi, lo;
+    at_split8(v + c8 * 8, hi, lo);
+    const int off = row * 128 + ((c8 ^ (row & 7)) << 4);
+    *reinterpret_cast<uint4*>(T + off) = hi;
+    *reinterpret_cast<uint4*>(T + plane_bytes + off) = lo;
+  }
+}
+
 struct AttnParams {
   int B, S, H, Hkv;
   float scale_log2;               // softmax scale * log2(e)
@@ -187,35 +222,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
       tmem_ld_wait();
       const int key0 = j * AT_BK;
       float mx = -INFINITY;
+      if (key0 + AT_BK - 1 <= q0) {                      // tile entirely left of the diagonal: nothing to mask
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        s[c] = (key0 + c <= qi) ? s[c] * c1 : -INFINITY;
-        mx = fmaxf(mx, s[c]);
+        for (int c = 0; c < 64; ++c) { s[c] *= c1; mx = fmaxf(mx, s[c]); }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) {
+          s[c] = (key0 + c <= qi) ? s[c] * c1 : -INFINITY;
+          mx = fmaxf(mx, s[c]);
+        }
       }
       const float m_new = fmaxf(m, mx);                // finite from the first tile on (key 0 is always visible)
-      const float corr = exp2f(m - m_new);
+      const float corr = at_exp2(m - m_new);
       float lsum = 0.f;
 #pragma unroll
       for (int c = 0; c < 64; ++c) {
-        s[c] = exp2f(s[c] - m_new);
-        lsum += s[c];
+        const float e = at_exp2(s[c] - m_new);
+        lsum += e;
+        s[c] = e * AT_P_SCALE;
       }
       l = l * corr + lsum;
       m = m_new;
-      // P_j as fp16 planes, K-major with the 128-byte swizzle (16-byte chunk c8 of row r sits at c8 ^ (r & 7))
-#pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8) {
-        uint16_t hi[8], lo[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) split_f16(s[c8 * 8 + e] * AT_P_SCALE, hi[e], lo[e]);
-        const int off = row * 128 + ((c8 ^ (row & 7)) << 4);
-        *reinterpret_cast<uint4*>(Ps + off) =
-            make_uint4(hi[0] | ((uint32_t)hi[1] << 16), hi[2] | ((uint32_t)hi[3] << 16), hi[4] | ((uint32_t)hi[5] << 16),
-                       hi[6] | ((uint32_t)hi[7] << 16));
-        *reinterpret_cast<uint4*>(Ps + Cfg::P_PLANE + off) =
-            make_uint4(lo[0] | ((uint32_t)lo[1] << 16), lo[2] | ((uint32_t)lo[3] << 16), lo[4] | ((uint32_t)lo[5] << 16),
-                       lo[6] | ((uint32_t)lo[7] << 16));
-      }
+      // P_j (x 2^14) as fp16 planes in the layout the MMA reads
+      at_store_planes(Ps, Cfg::P_PLANE, row, s);
       fence_proxy_async();
       tc_fence_before_sync();
       mbar_arrive(&p_full);
@@ -307,23 +336,6 @@ struct AtBwdCfg {
   static constexpr int SMEM_BYTES = OFF_T + 2 * T_PLANE + 1024;
   static constexpr float KAPPA = (D == 128) ? 5.9604644775390625e-8f /*2^-24*/ : 1.1920928955078125e-7f /*2^-23*/;
 };
-
-// 64 fp32 values of this thread's row -> (hi, lo) fp16 planes of a [128][64] K-major swizzled tile
-__device__ __forceinline__ void at_store_planes(unsigned char* T, int plane_bytes, int row, const float* v) {
-#pragma unroll
-  for (int c8 = 0; c8 < 8; ++c8) {
-    uint16_t hi[8], lo[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) split_f16(v[c8 * 8 + e], hi[e], lo[e]);
-    const int off = row * 128 + ((c8 ^ (row & 7)) << 4);
-    *reinterpret_cast<uint4*>(T + off) =
-        make_uint4(hi[0] | ((uint32_t)hi[1] << 16), hi[2] | ((uint32_t)hi[3] << 16), hi[4] | ((uint32_t)hi[5] << 16),
-                   hi[6] | ((uint32_t)hi[7] << 16));
-    *reinterpret_cast<uint4*>(T + plane_bytes + off) =
-        make_uint4(lo[0] | ((uint32_t)lo[1] << 16), lo[2] | ((uint32_t)lo[3] << 16), lo[4] | ((uint32_t)lo[5] << 16),
-                   lo[6] | ((uint32_t)lo[7] << 16));
-  }
-}
 
 // drain a [128 lanes x D] fp32 accumulator from TMEM, scale it and store rows [row0, row0 + 128) x [col0, col0 + D)
 // of a row-major matrix; rows >= row_limit are skipped.  stg: this warp's 32 x 32 float staging tile.
@@ -481,7 +493,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
           const int cc = half * 32 + c;
-          const float pr = (live && key0 + cc <= qi) ? exp2f(s[cc] * c1 - lse) : 0.f;
+          const float pr = (live && key0 + cc <= qi) ? at_exp2(s[cc] * c1 - lse) : 0.f;
           s[cc] = pr * (dp[c] - del_raw) * Cfg::KAPPA;
         }
       }
@@ -658,7 +670,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
 #pragma unroll
       for (int c = 0; c < 64; ++c) {
         const int qi = i * 64 + c;
-        s[c] = (qi < p.S && key <= qi && key < p.S) ? exp2f(s[c] * c1 - col_lse[t & 1][c]) : 0.f;   // P^T
+        s[c] = (qi < p.S && key <= qi && key < p.S) ? at_exp2(s[c] * c1 - col_lse[t & 1][c]) : 0.f;   // P^T
       }
       // the buffer's previous content (dS^T of step t-1) was consumed: qd_empty(t-1) preceded qd_full(t) <= s_full(t)
       {
@@ -722,6 +734,108 @@ __global__ void attn_delta_kernel(const float* __restrict__ dO, const float* __r
   if ((threadIdx.x & 31) == 0) {
     const int b = (int)(tok / S), q = (int)(tok % S);
     delta[((int64_t)b * H + h) * S + q] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ operand preparation
+// q, k, v leave their projections as fp32 [tokens, heads * D]; the attention kernels want RoPE applied to q and k
+// and all three as tensor-scaled fp16 planes.  Done separately that is two RoPE passes (read + write each) and three
+// split calls of two passes each (maximum, then planes).  Here: ONE pass for the three maxima (a rotation grows a
+// pair by at most sqrt(2), so the scale of the rotated tensor follows from the maximum before the rotation with
+// half a bit of headroom) and ONE pass that rotates, scales, splits and writes the planes; the rotated fp32 q / k
+// are never written -- nothing else reads them.
+__global__ void __launch_bounds__(256)
+attn_absmax3_kernel(const float4* __restrict__ q, int64_t nq4, const float4* __restrict__ k, int64_t nk4,
+                    const float4* __restrict__ v, int64_t nv4, uint32_t* __restrict__ ws) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float m[3] = {0.f, 0.f, 0.f};
+  const float4* src[3] = {q, k, v};
+  const int64_t n4[3] = {nq4, nk4, nv4};
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+    for (int64_t i = tid; i < n4[a]; i += stride) {
+      const float4 x = ldg_stream(src[a] + i);
+      const float y = fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w)));
+      if (y == y) m[a] = fmaxf(m[a], y);
+    }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float w = warp_max(m[a]);
+    if ((threadIdx.x & 31) == 0 && w > 0.f) atomicMax(ws + a, __float_as_uint(w));
+  }
+}
+
+struct PrepTensor {
+  const float* src;       // [tokens][heads * D]
+  uint16_t* planes;       // [2][tokens][pitch]
+  float* inv;             // [n_inv]
+  int heads, pitch, n_inv, rope;
+  int64_t items_per_token;   // rope: heads * D / 16 pair groups of 8; plain: heads * D / 8
+};
+
+__global__ void __launch_bounds__(256)
+attn_rope_split_kernel(PrepTensor tq, PrepTensor tk, PrepTensor tv, int64_t tokens, int seq, int D,
+                       const float* __restrict__ cosp, const float* __restrict__ sinp, int64_t cs_batch,
+                       const uint32_t* __restrict__ ws) {
+  const PrepTensor T[3] = {tq, tk, tv};
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = D >> 1;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const PrepTensor& P = T[a];
+    float sc, inv;
+    scale_from_max(__uint_as_float(ws[a]) * (P.rope ? 1.5f : 1.f), sc, inv);
+    for (int64_t i = tid; i < P.n_inv; i += stride) P.inv[i] = inv;
+    const int64_t total = tokens * P.items_per_token;
+    const int64_t plane = tokens * (int64_t)P.pitch;
+    const int cols = P.heads * D;
+    for (int64_t i = tid; i < total; i += stride) {
+      const int64_t t = i / P.items_per_token;
+      const int rem = (int)(i - t * P.items_per_token);
+      if (!P.rope) {
+        const int c = rem * 8;
+        const float4 a0 = ldg_stream(reinterpret_cast<const float4*>(P.src + t * cols + c));
+        const float4 a1 = ldg_stream(reinterpret_cast<const float4*>(P.src + t * cols + c + 4));
+        const float x[8] = {a0.x * sc, a0.y * sc, a0.z * sc, a0.w * sc, a1.x * sc, a1.y * sc, a1.z * sc, a1.w * sc};
+        uint4 hi, lo;
+        at_split8(x, hi, lo);
+        *reinterpret_cast<uint4*>(P.planes + t * P.pitch + c) = hi;
+        *reinterpret_cast<uint4*>(P.planes + plane + t * P.pitch + c) = lo;
+        continue;
+      }
+      const int groups = half >> 3;                      // groups of 8 pairs per head
+      const int h = rem / groups, j = (rem - h * groups) * 8;
+      const int64_t b = t / seq;
+      const int s = (int)(t - b * seq);
+      const float* cr = cosp + b * cs_batch + (int64_t)s * D;
+      const float* sr = sinp + b * cs_batch + (int64_t)s * D;
+      const float* p1 = P.src + t * cols + h * D + j;
+      float x1[8], x2[8], c1[8], c2[8], s1[8], s2[8], o1[8], o2[8];
+#pragma unroll
+      for (int e = 0; e < 8; e += 4) {
+        *reinterpret_cast<float4*>(x1 + e) = ldg_stream(reinterpret_cast<const float4*>(p1 + e));
+        *reinterpret_cast<float4*>(x2 + e) = ldg_stream(reinterpret_cast<const float4*>(p1 + half + e));
+        *reinterpret_cast<float4*>(c1 + e) = __ldg(reinterpret_cast<const float4*>(cr + j + e));
+        *reinterpret_cast<float4*>(c2 + e) = __ldg(reinterpret_cast<const float4*>(cr + half + j + e));
+        *reinterpret_cast<float4*>(s1 + e) = __ldg(reinterpret_cast<const float4*>(sr + j + e));
+        *reinterpret_cast<float4*>(s2 + e) = __ldg(reinterpret_cast<const float4*>(sr + half + j + e));
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        o1[e] = (x1[e] * c1[e] - x2[e] * s1[e]) * sc;   // same expression as rope_kernel (layer_ops.cu), then the scale
+        o2[e] = (x2[e] * c2[e] + x1[e] * s2[e]) * sc;
+      }
+      uint4 hi, lo;
+      uint16_t* d = P.planes + t * P.pitch + h * D + j;
+      at_split8(o1, hi, lo);
+      *reinterpret_cast<uint4*>(d) = hi;
+      *reinterpret_cast<uint4*>(d + plane) = lo;
+      at_split8(o2, hi, lo);
+      *reinterpret_cast<uint4*>(d + half) = hi;
+      *reinterpret_cast<uint4*>(d + half + plane) = lo;
+    }
   }
 }
 
@@ -836,4 +950,39 @@ extern "C" int grasp_attn_bwd(const void* q_planes, const float* inv_q, const vo
   prm.lse2 = lse2; prm.dq = dq; prm.dk = dk; prm.dv = dv;
   return D == 128 ? attn_bwd_launch<128>(q_planes, k_planes, v_planes, do_planes, dO, O, prm, delta_ws, stream)
                   : attn_bwd_launch<64>(q_planes, k_planes, v_planes, do_planes, dO, O, prm, delta_ws, stream);
+}
+
+extern "C" int grasp_attn_prep_qkv(const float* q, const float* k, const float* v, int64_t tokens, int64_t seq, int H,
+                                   int Hkv, int D, const float* cosp, const float* sinp, int64_t cs_batch, void* q_planes,
+                                   float* q_inv, void* k_planes, float* k_inv, void* v_planes, float* v_inv, void* ws,
+                                   void* stream) {
+  if (!q || !k || !v || !cosp || !sinp || !q_planes || !k_planes || !v_planes || !q_inv || !k_inv || !v_inv || !ws)
+    return bad_arg("attn_prep: null");
+  if (tokens <= 0 || seq <= 0 || tokens % seq || H <= 0 || Hkv <= 0 || (D != 64 && D != 128))
+    return bad_arg("attn_prep: tokens/seq/heads/head_dim");
+  if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+       reinterpret_cast<uintptr_t>(cosp) | reinterpret_cast<uintptr_t>(sinp)) & 15 || (cs_batch & 3))
+    return bad_arg("attn_prep: tensors must be 16-byte aligned");
+  if ((reinterpret_cast<uintptr_t>(q_planes) | reinterpret_cast<uintptr_t>(k_planes) | reinterpret_cast<uintptr_t>(v_planes)) & 1023)
+    return bad_arg("attn_prep: planes must be 1024-byte aligned");
+  int rc = check_cuda(cudaMemsetAsync(ws, 0, 12, (cudaStream_t)stream), "attn_prep memset");
+  if (rc) return rc;
+  const int64_t nq4 = tokens * H * D / 4, nk4 = tokens * Hkv * D / 4;
+  const int grid = sm_count() * 8;
+  GRASP_LAUNCH(attn_absmax3_kernel, dim3(grid), dim3(256), 0, stream, reinterpret_cast<const float4*>(q), nq4,
+               reinterpret_cast<const float4*>(k), nk4, reinterpret_cast<const float4*>(v), nk4, static_cast<uint32_t*>(ws));
+  auto make = [&](const float* src, void* planes, float* inv, int heads, int rope) {
+    PrepTensor t{};
+    t.src = src; t.planes = static_cast<uint16_t*>(planes); t.inv = inv; t.heads = heads;
+    t.pitch = (int)plane_pitch((int64_t)heads * D);
+    t.n_inv = (int)(tokens > (int64_t)heads * D ? tokens : (int64_t)heads * D);
+    t.rope = rope;
+    t.items_per_token = rope ? (int64_t)heads * D / 16 : (int64_t)heads * D / 8;
+    return t;
+  };
+  GRASP_LAUNCH(attn_rope_split_kernel, dim3(grid), dim3(256), 0, stream, make(q, q_planes, q_inv, H, 1),
+               make(k, k_planes, k_inv, Hkv, 1), make(v, v_planes, v_inv, Hkv, 0), tokens, (int)seq, D, cosp, sinp, cs_batch,
+               static_cast<const uint32_t*>(ws));
+  GRASP_CHECK_LAST("attn_prep kernels");
+  return 0;
 }

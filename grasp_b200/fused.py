@@ -115,6 +115,8 @@ class CudaBackend:
             return dg, du, ops.split_f16(dg, _lib.SCALE_ROWS), ops.split_f16(du, _lib.SCALE_ROWS)
         return ops.swiglu_bwd(dh, g, u, inplace=True, want_grads=keep_grads, want_operands=True)
 
+    attn_prep = staticmethod(ops.attn_prep_qkv)
+
     # -- row kernels
     rmsnorm_fwd = staticmethod(ops.rmsnorm_fwd)
     rmsnorm_bwd = staticmethod(ops.rmsnorm_bwd)
@@ -275,9 +277,16 @@ class FusedLlama:
         v = self.lin_fwd(att.v_proj, xo, tag=i)
         del xo
         H, Hkv = q.shape[1] // D, k.shape[1] // D
-        be.rope_(q, S, H, D, cos, sin)
-        be.rope_(k, S, Hkv, D, cos, sin)
-        a, actx = sdpa_fwd(q, k, v, B, S, H, Hkv, D, att.scaling, keep)
+        if _own_attention(q, D) and hasattr(be, "attn_prep"):
+            # RoPE + operand planes of q, k, v in two passes, then the tensor-core attention
+            qo, ko, vo = be.attn_prep(q, k, v, S, H, Hkv, D, cos, sin)
+            a, actx = ops.attn_fwd_prepared(qo, ko, vo, B, S, H, Hkv, D, att.scaling)
+            actx = ("grasp", actx) if keep else None
+            del qo, ko, vo
+        else:
+            be.rope_(q, S, H, D, cos, sin)
+            be.rope_(k, S, Hkv, D, cos, sin)
+            a, actx = sdpa_fwd(q, k, v, B, S, H, Hkv, D, att.scaling, keep)
         x2 = self.lin_fwd(att.o_proj, be.prep(a), tag=i)
         x2 += x
         xn2, rstd2, xo2 = be.rmsnorm_fwd_op(x2, L.post_attention_layernorm.weight,

@@ -608,14 +608,44 @@ def attn_supported(head_dim: int) -> bool:
     return int(head_dim) in ATTN_HEAD_DIMS
 
 
-def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, S: int, H: int, Hkv: int, D: int, scale: float):
-    """Causal attention of [B*S, H*D] / [B*S, Hkv*D] activations (after RoPE).  Returns (out [B*S, H*D], ctx);
-    ctx carries what attn_bwd needs (operand planes of q, k, v, the output and the row log-sum-exps)."""
+def attn_prep_qkv(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, S: int, H: int, Hkv: int, D: int, cos: torch.Tensor,
+                  sin: torch.Tensor):
+    """Operands of attn_fwd_prepared from the projections as they leave their GEMMs: RoPE on q and k (cos / sin
+    [1 or B, S, D]), then tensor-scaled planes of the rotated q, k and of v.  q, k, v are left untouched."""
     lib = _lib.load()
-    dev = _need_cuda(q, k, v)
-    if q.shape != (B * S, H * D) or k.shape != (B * S, Hkv * D) or v.shape != k.shape:
+    dev = _need_cuda(q, k, v, cos, sin)
+    q, k, v = _rows2d(q, "q"), _rows2d(k, "k"), _rows2d(v, "v")
+    tokens = q.shape[0]
+    if q.shape[1] != H * D or k.shape != (tokens, Hkv * D) or v.shape != k.shape or tokens % S:
+        raise ValueError("attn_prep_qkv: q [tokens, H*D], k / v [tokens, Hkv*D], tokens a multiple of S")
+    cos, sin = _f32c(cos, "cos"), _f32c(sin, "sin")
+    if cos.shape[-2:] != (S, D) or sin.shape != cos.shape:
+        raise ValueError("attn_prep_qkv: cos/sin must be [*, S, head_dim]")
+    batch = cos.shape[0] if cos.dim() == 3 else 1
+    if batch != 1 and batch * S != tokens:
+        raise ValueError("attn_prep_qkv: cos/sin batch does not match the token count")
+    cs_batch = 0 if batch == 1 else S * D
+    qo = _new_operand(tokens, H * D, _lib.SCALE_TENSOR, dev)
+    ko = _new_operand(tokens, Hkv * D, _lib.SCALE_TENSOR, dev)
+    vo = _new_operand(tokens, Hkv * D, _lib.SCALE_TENSOR, dev)
+    ws = torch.empty(4, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        t0 = timers.start()
+        check(lib.grasp_attn_prep_qkv(q.data_ptr(), k.data_ptr(), v.data_ptr(), tokens, S, H, Hkv, D, cos.data_ptr(),
+                                      sin.data_ptr(), cs_batch, qo.planes, qo.inv.data_ptr(), ko.planes, ko.inv.data_ptr(),
+                                      vo.planes, vo.inv.data_ptr(), ws.data_ptr(), _stream()), "grasp_attn_prep_qkv")
+        timers.stop("grasp_rowops", t0, bytes_=(8.0 + 4.0) * (q.numel() + k.numel() + v.numel()))
+    return qo, ko, vo
+
+
+def attn_fwd_prepared(qo: Operand, ko: Operand, vo: Operand, B: int, S: int, H: int, Hkv: int, D: int, scale: float):
+    """Causal attention on prepared (RoPE'd, tensor-scaled) operands.  Returns (out [B*S, H*D], ctx for attn_bwd)."""
+    lib = _lib.load()
+    dev = qo.inv.device
+    if (qo.rows, qo.cols) != (B * S, H * D) or (ko.rows, ko.cols) != (B * S, Hkv * D) or (vo.rows, vo.cols) != (ko.rows, ko.cols):
         raise ValueError("attn_fwd: q [B*S, H*D], k / v [B*S, Hkv*D] expected")
-    qo, ko, vo = (split_f16(t, _lib.SCALE_TENSOR) for t in (q, k, v))
+    if not (qo.mode == ko.mode == vo.mode == _lib.SCALE_TENSOR):
+        raise ValueError("attn_fwd: operands must be tensor-scaled")
     out = torch.empty(B * S, H * D, dtype=torch.float32, device=dev)
     lse2 = torch.empty(B * H * S, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
@@ -624,6 +654,15 @@ def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, S: int, 
                                  B, S, H, Hkv, D, float(scale), out.data_ptr(), lse2.data_ptr(), _stream()), "grasp_attn_fwd")
         timers.stop("grasp_attn", t0, flops=2.0 * B * H * S * S * D, mma_per_flop=3.0)      # causal: half of 4 S^2 D
     return out, (qo, ko, vo, out, lse2, (B, S, H, Hkv, D, float(scale)))
+
+
+def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, S: int, H: int, Hkv: int, D: int, scale: float):
+    """Causal attention of [B*S, H*D] / [B*S, Hkv*D] activations (RoPE already applied)."""
+    _need_cuda(q, k, v)
+    if q.shape != (B * S, H * D) or k.shape != (B * S, Hkv * D) or v.shape != k.shape:
+        raise ValueError("attn_fwd: q [B*S, H*D], k / v [B*S, Hkv*D] expected")
+    qo, ko, vo = (split_f16(t, _lib.SCALE_TENSOR) for t in (q, k, v))
+    return attn_fwd_prepared(qo, ko, vo, B, S, H, Hkv, D, scale)
 
 
 def attn_bwd(ctx, d_out: torch.Tensor):

@@ -232,6 +232,13 @@ int grasp_ce_loss_bwd(float* logits, const int64_t* labels, const float* coef, i
  *   bwd: dq [B*S][H*D], dk / dv [B*S][Hkv*D] (summed over the query heads of a group), from dO (fp32 and its
  *        planes), the forward's out and lse2; delta_ws holds B*H*S floats.
  * ------------------------------------------------------------------------- */
+/* RoPE (transformers' apply_rotary_pos_emb, cos / sin as for grasp_rope_inplace) on q and k, and the tensor-scaled
+ * operand planes of the rotated q, k and of v, in two passes over the fp32 projections (which stay untouched).
+ * inv arrays as for GRASP_SCALE_TENSOR (max(tokens, heads*D) + 1 floats); ws: 16 bytes of scratch. */
+int grasp_attn_prep_qkv(const float* q, const float* k, const float* v, int64_t tokens, int64_t seq, int H, int Hkv,
+                        int D, const float* cos, const float* sin, int64_t cs_batch,
+                        void* q_planes, float* q_inv, void* k_planes, float* k_inv, void* v_planes, float* v_inv,
+                        void* ws, void* stream);
 int grasp_attn_fwd(const void* q_planes, const float* inv_q, const void* k_planes, const float* inv_k,
                    const void* v_planes, const float* inv_v, int B, int S, int H, int Hkv, int D, float scale,
                    float* out, float* lse2, void* stream);
