@@ -501,6 +501,12 @@ class LlamaRunner:
             self.cache, self.cache_key = {}, id(calib)
         wanted = sorted(set(layer_ids))
         need = [l for l in wanted if l not in self.cache]
+        if need and keep_only:
+            # make room first: of the entries that are not wanted only the sweep's starting point is of use
+            sources = [c for c in self.cache if c <= need[0]]
+            start = max(sources) if sources else None
+            for k in [k for k in self.cache if k not in wanted and k != start]:
+                del self.cache[k]
         if need:
             n = len(calib)
             probe = self.embed(calib.input_ids[:1])
@@ -545,16 +551,25 @@ class LlamaRunner:
                 del self.cache[k]      # checkpoints of the scoring pass served their purpose
 
     def _plan_checkpoints(self, calib: CalibrationSet, hidden_shape, element_size):
-        """Layers whose input is kept during the scoring pass: as many evenly spaced ones as fit in 40 % of
-        the store budget (the selected layers are unknown until scoring has finished)."""
+        """Layers whose input is kept during the scoring pass.  The selected layers are unknown until scoring has
+        finished, but block influence falls with depth (the reference's premise, and ShortGPT's finding): two
+        thirds of the slots go to the deepest layers, one per layer, the rest is spread evenly below them.  A kept
+        entry that turns out to be a selected layer IS its prefix cache (no recomputation); the others serve as
+        starting points for the sweep.  All slots but one of the store budget are used (entries that are not
+        needed are dropped before the sweep allocates anything)."""
         if not calib.input_ids.is_cuda:
             return []
         budget = self.plan_store(calib, hidden_shape, element_size)
-        count = int(min(self.n_layers - 1, (0.4 * budget) // max(self.store_per, 1)))
-        if count <= 0:
+        n_ck = int(min(self.n_layers - 1, budget // max(self.store_per, 1) - 1))
+        if n_ck <= 0:
             return []
-        stride = -(-self.n_layers // (count + 1))
-        return list(range(stride, self.n_layers, stride))
+        top = min((2 * n_ck + 2) // 3, self.n_layers - 1)
+        plan = list(range(self.n_layers - top, self.n_layers))
+        rest, below = n_ck - top, self.n_layers - top          # `rest` more entries among layers [1, below)
+        if rest > 0 and below > 1:
+            stride = -(-below // (rest + 1))
+            plan += list(range(stride, below, stride))[:rest]
+        return sorted(set(plan))
 
     # ---- stage 1 ------------------------------------------------------------------
     def block_influence(self, calib: CalibrationSet, scorer: "BlockInfluence"):

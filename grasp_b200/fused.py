@@ -24,6 +24,7 @@ that lives in tests/ -- the product backend below has no CPU path.
 """
 from __future__ import annotations
 
+import os
 import weakref
 from collections import OrderedDict
 from typing import Optional
@@ -146,7 +147,8 @@ def _sdpa(q, k, v, B, S, H, Hkv, D, scale):
 def _own_attention(q, D) -> bool:
     """The library's tensor-core attention applies (fp32 CUDA activations, head_dim 64 / 128); otherwise torch's
     scaled_dot_product_attention (library code) serves, e.g. for the 16 / 32-wide heads of the test models."""
-    return q.is_cuda and q.dtype == torch.float32 and ops.attn_supported(D)
+    return (q.is_cuda and q.dtype == torch.float32 and ops.attn_supported(D)
+            and os.environ.get("GRASP_B200_ATTN", "1") != "0")       # 0: torch's kernels everywhere (cross-check)
 
 
 def sdpa_fwd(q, k, v, B, S, H, Hkv, D, scale, keep):
