@@ -30,7 +30,7 @@ constexpr int TC_BK = 64;           // 64 bf16 = 128 bytes = one swizzle row
 constexpr int TC_THREADS = 192;
 constexpr int TC_A_TILE = TC_BM * TC_BK * 2;   // 16 KiB per plane
 
-enum { EPI_STORE = 0, EPI_SIGMA = 1 };
+enum { EPI_STORE = 0, EPI_SIGMA = 1, EPI_PLANES = 2 };
 
 struct TcParams {
   int M, N, K;
@@ -45,6 +45,15 @@ struct TcParams {
   const float* inv_sa;  // F16 planes: per-row inverse scale of A (M) and B (N); the accumulator is
   const float* inv_sb;  //   multiplied by inv_sa[m] * inv_sb[n] before the epilogue
   int kgroup;           // K blocks accumulated in one TMEM buffer before the epilogue drains it (0 = 1)
+  // EPI_PLANES: the result leaves as a prepared operand (fp16 hi / lo planes [2][M][out_pitch] + row scales) instead
+  // of fp32: the rank-k intermediate of a factor pair (SVDLinear, reference modeling_grasp.py:57-59) feeds the next
+  // GEMM directly.  The row scale comes from a bound, not from the row maximum (a tile sees only BN columns):
+  // |acc| <= K * 2^30 in plane units, so acc * out_scale with out_scale = 2^-16 / pow2ceil(K) stays below 2^14;
+  // out_inv[row] = inv_sa[row] * inv_sb[0] / out_scale (exact powers of two).  Needs a tensor-scaled B.
+  uint16_t* out_planes;
+  int64_t out_pitch, out_plane_stride;
+  float* out_inv;
+  float out_scale;
   int group_m;          // tile rasterisation: M blocks per super-row (see tile_coords)
   int staged;           // EPI_STORE fp32: transpose through shared memory, 128-byte row segments per store
 };
@@ -242,7 +251,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if constexpr (F16) {
         // undo the per-row power-of-two scaling of the fp16 planes (exact)
         const float ia = (row < p.M) ? p.inv_sa[row] : 0.f;
-        if (staged) {
+        if (staged || EPI == EPI_PLANES) {
           row_scale *= ia;                          // the column scales are applied after the transpose (8 vector loads
         } else {                                    // per lane and tile instead of 128 scalar ones)
 #pragma unroll
@@ -252,8 +261,34 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
         }
       }
+      if constexpr (EPI == EPI_PLANES) {
+        // (F16 only) planes of acc * out_scale: the plane scales of A and B stay folded into out_inv[row]
+        if (row < p.M) {
+          if (n_blk == 0 && half == 0) p.out_inv[row] = p.inv_sa[row] * p.inv_sb[0] / p.out_scale;
+          uint16_t* hi_row = p.out_planes + (int64_t)row * p.out_pitch;
+#pragma unroll
+          for (int c8 = 0; c8 < 16; ++c8) {
+            const int col = n0 + half * 128 + c8 * 8;
+            if (col < p.out_pitch) {            // columns in [N, pitch) hold exact zeros (zero-filled B rows)
+              uint32_t h[4], l[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float a = racc[c8 * 8 + 2 * e] * p.out_scale, b2 = racc[c8 * 8 + 2 * e + 1] * p.out_scale;
+                const __half2 h2 = __floats2half2_rn(a, b2);
+                const float2 f = __half22float2(h2);
+                const __half2 l2 = __floats2half2_rn(a - f.x, b2 - f.y);
+                h[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                l[e] = *reinterpret_cast<const uint32_t*>(&l2);
+              }
+              *reinterpret_cast<uint4*>(hi_row + col) = make_uint4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<uint4*>(hi_row + p.out_plane_stride + col) = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+          }
+        }
+      }
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
+        if constexpr (EPI == EPI_PLANES) break;
         float* v = &racc[c * 32];
         const int col0 = n0 + half * 128 + c * 32;
         if constexpr (EPI == EPI_STORE) {
@@ -1258,6 +1293,38 @@ int tc_gemm_planes(int64_t M, int64_t N, int64_t K, float alpha, const void* Ap,
   }
   if (b_kn) return launch_core<2, 128, EPI_STORE, 1, 1>(A16, B16, prm, stream);
   return launch_core<2, 128, EPI_STORE, 0, 1>(A16, B16, prm, stream);
+}
+
+static float pow2_at_least(int64_t k) {
+  float p = 1.f;
+  while (p < (float)k) p *= 2.f;
+  return p;
+}
+
+// out = A op(B) as a prepared operand (row-scaled planes [2][M][pitch(N)] + inv [M]); B must be tensor-scaled
+int tc_gemm_planes_out(int64_t M, int64_t N, int64_t K, const void* Ap, const float* inv_a, const void* Bp, int b_kn,
+                       const float* inv_b, void* out_planes, float* out_inv, void* stream) {
+  if (!dims_ok(M, N, K)) return bad_arg("gemm_planes_out: M/N/K");
+  if ((reinterpret_cast<uintptr_t>(Ap) & 1023) || (reinterpret_cast<uintptr_t>(Bp) & 1023) ||
+      (reinterpret_cast<uintptr_t>(out_planes) & 1023))
+    return bad_arg("gemm_planes_out: planes must be 1024-byte aligned");
+  TcParams prm{};
+  prm.M = (int)M; prm.N = (int)N; prm.K = (int)K;
+  prm.alpha = 1.f; prm.beta = 0.f;
+  prm.inv_sa = inv_a; prm.inv_sb = inv_b;
+  prm.out_planes = static_cast<uint16_t*>(out_planes);
+  prm.out_pitch = kp_of(N);
+  prm.out_plane_stride = M * (int64_t)kp_of(N);
+  prm.out_inv = out_inv;
+  prm.out_scale = 1.52587890625e-05f /*2^-16*/ / pow2_at_least(K);
+  const __nv_bfloat16* A16 = static_cast<const __nv_bfloat16*>(Ap);
+  const __nv_bfloat16* B16 = static_cast<const __nv_bfloat16*>(Bp);
+  if (wide_tiles(M, N, K)) {
+    if (b_kn) return launch_core<2, 256, EPI_PLANES, 1, 1>(A16, B16, prm, stream);
+    return launch_core<2, 256, EPI_PLANES, 0, 1>(A16, B16, prm, stream);
+  }
+  if (b_kn) return launch_core<2, 128, EPI_PLANES, 1, 1>(A16, B16, prm, stream);
+  return launch_core<2, 128, EPI_PLANES, 0, 1>(A16, B16, prm, stream);
 }
 
 int tc_sigma_partials(const float* U, const float* G, const float* Vh, int64_t out, int64_t in, int64_t r, int prec,

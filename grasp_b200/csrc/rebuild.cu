@@ -17,6 +17,9 @@ int tc_split_f16(const float* src, int64_t ld, int64_t rows, int64_t cols, int s
 int tc_gemm_planes(int64_t M, int64_t N, int64_t K, float alpha, const void* Ap, const float* inv_a, const void* Bp,
                    int b_kn, const float* inv_b, float beta, float* C, int64_t ldc, void* stream);
 
+int tc_gemm_planes_out(int64_t M, int64_t N, int64_t K, const void* Ap, const float* inv_a, const void* Bp, int b_kn,
+                       const float* inv_b, void* out_planes, float* out_inv, void* stream);
+
 // Uk[a][j] = U[a][idx[j]] * su(j),  j < kp (zero beyond k);  su = 1 (mode 0) or sqrt(S) (mode 1)
 __global__ void gather_cols_kernel(const float* __restrict__ U, const float* __restrict__ S,
                                    const int64_t* __restrict__ idx, int64_t out, int64_t r, int64_t k, int64_t kp,
@@ -151,4 +154,11 @@ extern "C" int grasp_gemm_f16x3_planes(int64_t M, int64_t N, int64_t K, float al
   if (!A_planes || !B_planes || !inv_a || !inv_b || !C) return bad_arg("gemm_planes: null");
   if (ldc < N) return bad_arg("gemm_planes: leading dimension");
   return tc_gemm_planes(M, N, K, alpha, A_planes, inv_a, B_planes, b_kn, inv_b, beta, C, ldc, stream);
+}
+
+extern "C" int grasp_gemm_f16x3_planes_out(int64_t M, int64_t N, int64_t K, const void* A_planes, const float* inv_a,
+                                           const void* B_planes, int b_kn, const float* inv_b, void* out_planes,
+                                           float* out_inv, void* stream) {
+  if (!A_planes || !B_planes || !inv_a || !inv_b || !out_planes || !out_inv) return bad_arg("gemm_planes_out: null");
+  return tc_gemm_planes_out(M, N, K, A_planes, inv_a, B_planes, b_kn, inv_b, out_planes, out_inv, stream);
 }

@@ -92,6 +92,13 @@ class CudaBackend:
     def mm_nn(self, dyo, wo, out=None, beta=0.0):         # dy W
         return ops.gemm_planes(dyo, wo, b_kn=True, beta=beta, C_out=out)
 
+    # the rank-k intermediate of a factor pair leaves its GEMM as the operand of the next one
+    def mm_nt_op(self, xo, wo):
+        return ops.gemm_planes_to_operand(xo, wo, b_kn=False)
+
+    def mm_nn_op(self, dyo, wo):
+        return ops.gemm_planes_to_operand(dyo, wo, b_kn=True)
+
     def harvest(self, dy, x, G):                          # G (+)= dy^T x
         if G is None:
             return ops.gemm(dy, x, ta=True)
@@ -236,8 +243,11 @@ class FusedLlama:
     def lin_fwd(self, mod, xo, tag=None):
         be, kind = self.be, linear_kind(mod)
         if kind == "svd":
-            t = be.mm_nt(xo, be.wprep(mod.InLinear.weight, tag))
-            y = be.mm_nt(be.prep(t), be.wprep(mod.OutLinear.weight, tag))
+            if hasattr(be, "mm_nt_op"):
+                to = be.mm_nt_op(xo, be.wprep(mod.InLinear.weight, tag))
+            else:
+                to = be.prep(be.mm_nt(xo, be.wprep(mod.InLinear.weight, tag)))
+            y = be.mm_nt(to, be.wprep(mod.OutLinear.weight, tag))
             bias = mod.OutLinear.bias
         else:
             y = be.mm_nt(xo, be.wprep(self._weight(mod, kind), tag))
@@ -249,8 +259,11 @@ class FusedLlama:
     def lin_bwd(self, mod, dyo, out=None, beta=0.0, tag=None):
         be, kind = self.be, linear_kind(mod)
         if kind == "svd":
-            dt = be.mm_nn(dyo, be.wprep(mod.OutLinear.weight, tag))
-            return be.mm_nn(be.prep(dt), be.wprep(mod.InLinear.weight, tag), out=out, beta=beta)
+            if hasattr(be, "mm_nn_op"):
+                dto = be.mm_nn_op(dyo, be.wprep(mod.OutLinear.weight, tag))
+            else:
+                dto = be.prep(be.mm_nn(dyo, be.wprep(mod.OutLinear.weight, tag)))
+            return be.mm_nn(dto, be.wprep(mod.InLinear.weight, tag), out=out, beta=beta)
         return be.mm_nn(dyo, be.wprep(self._weight(mod, kind), tag), out=out, beta=beta)
 
     def harvest(self, mod, dy, x):

@@ -461,6 +461,26 @@ def gemm_planes(a: Operand, b: Operand, b_kn: bool = False, alpha: float = 1.0, 
     return C_out
 
 
+def gemm_planes_to_operand(a: Operand, b: Operand, b_kn: bool = False) -> Operand:
+    """A op(B) handed over as a prepared (row-scaled) operand: the first GEMM of a factor pair.  B tensor-scaled."""
+    lib = _lib.load()
+    M, K = a.rows, a.cols
+    K2, N = (b.rows, b.cols) if b_kn else (b.cols, b.rows)
+    if K != K2:
+        raise ValueError(f"inner dimensions differ: {K} vs {K2}")
+    if b.mode != _lib.SCALE_TENSOR:
+        raise ValueError("gemm_planes_to_operand needs a tensor-scaled B")
+    dev = a.inv.device
+    out = _new_operand(M, N, _lib.SCALE_ROWS, dev)
+    with torch.cuda.device(dev):
+        t0 = timers.start()
+        check(lib.grasp_gemm_f16x3_planes_out(M, N, K, a.planes, a.inv.data_ptr(), b.planes, int(bool(b_kn)),
+                                              b.inv.data_ptr(), out.planes, out.inv.data_ptr(), _stream()),
+              "grasp_gemm_f16x3_planes_out")
+        timers.stop("grasp_gemm_f16x3_planes", t0, flops=2.0 * M * N * K, mma_per_flop=3.0)
+    return out
+
+
 # ------------------------------------------------------- decoder-layer row kernels
 def _rows2d(t: torch.Tensor, name: str) -> torch.Tensor:
     if t.dim() != 2:

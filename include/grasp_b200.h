@@ -186,6 +186,15 @@ int    grasp_gemm_f16x3_planes(int64_t M, int64_t N, int64_t K, float alpha,
                                const void* B_planes, int b_kn, const float* inv_b,
                                float beta, float* C, int64_t ldc, void* stream);
 
+/* (f2) the first GEMM of a factor pair (SVDLinear.forward, modeling_grasp.py:57-59: OutLinear(InLinear(x)), and the
+ * mirrored backward): out = A op(B) leaves as a prepared operand -- row-scaled planes [2][M][pitch(N)] + inv [M] --
+ * that the second GEMM consumes, so the [tokens, k] intermediate is never written in fp32 nor split by a pre-pass.
+ * B must be tensor-scaled (weights are). */
+int    grasp_gemm_f16x3_planes_out(int64_t M, int64_t N, int64_t K,
+                                   const void* A_planes, const float* inv_a,
+                                   const void* B_planes, int b_kn, const float* inv_b,
+                                   void* out_planes, float* out_inv, void* stream);
+
 /* ---------------------------------------------------------------------------
  * (f1) row-wise pieces of the LLaMA decoder layer the calibration passes run
  * between the GEMMs (the reference leaves them to transformers' eager modules,

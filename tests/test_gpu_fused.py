@@ -40,6 +40,35 @@ def test_gemm_planes_forward_and_backward_forms(cuda, M, N, K):
         ops.gemm_planes(dyo, wr, b_kn=True)      # a [K, N] operand needs one scale for the whole tensor
 
 
+@pytest.mark.parametrize("M,K,k,N", [(300, 1000, 204, 520), (1030, 4096, 298, 4096), (129, 72, 22, 64), (2300, 11008, 298, 4096)])
+def test_factor_pair_without_an_fp32_intermediate(cuda, M, K, k, N):
+    """SVDLinear forward OutLinear(InLinear(x)) (reference modeling_grasp.py:57-59) and its backward
+    dy OutW InW: the first GEMM hands its [tokens, k] result over as operand planes (grasp_gemm_f16x3_planes_out),
+    the second consumes them -- against fp64, and against the route through an fp32 intermediate + split."""
+    from grasp_b200 import _lib, ops
+    g = torch.Generator().manual_seed(M + K + k + N)
+    x = torch.randn(M, K, generator=g).to(cuda)
+    in_w = (torch.randn(k, K, generator=g) * 0.02).to(cuda)        # InLinear.weight  [k, in]
+    out_w = (torch.randn(N, k, generator=g) * 0.05).to(cuda)       # OutLinear.weight [out, k]
+    dy = (torch.randn(M, N, generator=g) * 1e-3).to(cuda)
+    xo, dyo = ops.split_f16(x), ops.split_f16(dy)
+    wi, wo = ops.split_f16(in_w, _lib.SCALE_TENSOR), ops.split_f16(out_w, _lib.SCALE_TENSOR)
+    # forward
+    to = ops.gemm_planes_to_operand(xo, wi)
+    assert (to.rows, to.cols, to.mode) == (M, k, _lib.SCALE_ROWS)
+    y = ops.gemm_planes(to, wo)
+    y_ref = (x.double() @ in_w.double().t()) @ out_w.double().t()
+    y_two = ops.gemm_planes(ops.split_f16(ops.gemm_planes(xo, wi)), wo)
+    assert rel(y, y_ref) < 2e-6 and rel(y, y_two) < 2e-6
+    # backward: dx = (dy OutW) InW, both weights as [K, N] operands
+    dto = ops.gemm_planes_to_operand(dyo, wo, b_kn=True)
+    dx = ops.gemm_planes(dto, wi, b_kn=True)
+    dx_ref = (dy.double() @ out_w.double()) @ in_w.double()
+    assert rel(dx, dx_ref) < 2e-6
+    with pytest.raises(ValueError):
+        ops.gemm_planes_to_operand(xo, ops.split_f16(in_w, _lib.SCALE_ROWS))     # the bound needs one scale for B
+
+
 def test_operands_with_more_than_65535_rows(cuda):
     """lm_head of a 128k-token vocabulary: the row index must not sit on a 16-bit grid dimension."""
     from grasp_b200 import _lib, ops
