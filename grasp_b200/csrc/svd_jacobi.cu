@@ -864,6 +864,25 @@ svd_orth_defect_kernel(const float* __restrict__ T, int64_t ld, int r, float tol
   if ((threadIdx.x & 31) == 0 && m > tol) atomicOr(fail, 2u);
 }
 
+// G[i][i] += rel * mean_i G[i][i]   (one CTA)
+__global__ void __launch_bounds__(1024)
+svd_shift_diag_kernel(float* __restrict__ G, int64_t ld, int r, float rel) {
+  __shared__ float red[32];
+  __shared__ float shift;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < r; i += blockDim.x) acc += G[(int64_t)i * ld + i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) shift = rel * v / (float)r;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < r; i += blockDim.x) G[(int64_t)i * ld + i] += shift;
+}
+
 struct IcCtx {
   void* stream;
   void* gws;
@@ -920,7 +939,10 @@ static size_t pre_shared_bytes(int64_t r, int64_t L) {
   return (size_t)3 * r * r * 4 + (size_t)r * L * 4 + pre_gws_bytes(r, L) + 4 * 1024;
 }
 
-// Y0 = A (trans = 0, A is r x L) or A^T (trans = 1, A is L x r).  Writes Lm [r][r] and Q [r][L].
+// Y0 = A (trans = 0, A is r x L) or A^T (trans = 1, A is L x r).  Writes Lm [r][r] = Y0 Q^T and Q [r][L].
+// Three Cholesky passes: the first on the Gram shifted by 2e-5 of its mean diagonal, which keeps the fp32
+// factorisation positive definite when cond(Y0)^2 > 1 / eps (square Gaussian matrices: cond ~ 3e4) and leaves a Q1
+// of condition ~60; the second and third (unshifted) bring the rows of Q to orthonormality at rounding level.
 static int svd_precondition(const float* A, int64_t lda, int trans, int r, int L, float* Lm, float* Q, uint32_t* fail,
                             const PreShared& sh, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
@@ -936,22 +958,28 @@ static int svd_precondition(const float* A, int64_t lda, int trans, int r, int L
   int rc = check_cuda(cudaMemsetAsync(fail, 0, 4, st), "svd pre memset");
   if (rc) return rc;
   const size_t rr = (size_t)r * r * 4;
-  // op(Y0) for the GEMM: Y0 as the left operand is (ta = trans, A); Y0 as op(B) = K x N is (tb = trans ? 1 : 0, A)
-  // G = Y0 Y0^T
+  float shift_rel = 2e-5f;
+  if (const char* e = getenv("GRASP_SVD_PRECOND_SHIFT")) shift_rel = (float)atof(e);
+  // pass 1: G = Y0 Y0^T (+ shift), Q1 = inv(chol(G)) Y0.  Y0 as the left operand is (ta = trans, A); as op(B) = K x N
+  // it is (tb = trans ? 1 : 0, A)
   rc = tc_gemm_f32(trans, trans ? 0 : 1, r, r, L, 1.f, A, lda, A, lda, 0.f, sh.G, r, 0, P, sh.gws, sh.gws_bytes, stream);
   if (rc) return rc;
+  GRASP_LAUNCH(svd_shift_diag_kernel, dim3(1), dim3(1024), 0, st, sh.G, (int64_t)r, r, shift_rel);
   rc = check_cuda(cudaMemsetAsync(sh.M, 0, rr, st), "svd pre memset"); if (rc) return rc;
   rc = invchol_rec(sh.G, r, r, sh.M, r, sh.scratch, c); if (rc) return rc;
-  // Q1 = M1 Y0
-  rc = tc_gemm_f32(0, trans ? 1 : 0, r, L, r, 1.f, sh.M, r, A, lda, 0.f, sh.Q1, L, 0, P, sh.gws, sh.gws_bytes, stream);
+  rc = tc_gemm_f32(0, trans ? 1 : 0, r, L, r, 1.f, sh.M, r, A, lda, 0.f, Q, L, 0, P, sh.gws, sh.gws_bytes, stream);
   if (rc) return rc;
-  // second pass on Q1 (orthonormal to ~eps cond^2 after the first)
-  rc = tc_gemm_f32(0, 1, r, r, L, 1.f, sh.Q1, L, sh.Q1, L, 0.f, sh.G, r, 0, P, sh.gws, sh.gws_bytes, stream);
-  if (rc) return rc;
-  rc = check_cuda(cudaMemsetAsync(sh.M, 0, rr, st), "svd pre memset"); if (rc) return rc;
-  rc = invchol_rec(sh.G, r, r, sh.M, r, sh.scratch, c); if (rc) return rc;
-  rc = tc_gemm_f32(0, 0, r, L, r, 1.f, sh.M, r, sh.Q1, L, 0.f, Q, L, 0, P, sh.gws, sh.gws_bytes, stream);
-  if (rc) return rc;
+  // passes 2 and 3: Q -> Q1 -> Q
+  for (int pass = 0; pass < 2; ++pass) {
+    float* src = pass == 0 ? Q : sh.Q1;
+    float* dst = pass == 0 ? sh.Q1 : Q;
+    rc = tc_gemm_f32(0, 1, r, r, L, 1.f, src, L, src, L, 0.f, sh.G, r, 0, P, sh.gws, sh.gws_bytes, stream);
+    if (rc) return rc;
+    rc = check_cuda(cudaMemsetAsync(sh.M, 0, rr, st), "svd pre memset"); if (rc) return rc;
+    rc = invchol_rec(sh.G, r, r, sh.M, r, sh.scratch, c); if (rc) return rc;
+    rc = tc_gemm_f32(0, 0, r, L, r, 1.f, sh.M, r, src, L, 0.f, dst, L, 0, P, sh.gws, sh.gws_bytes, stream);
+    if (rc) return rc;
+  }
   // orthonormality of Q (also catches NaN / Inf from a failed factorisation)
   rc = tc_gemm_f32(0, 1, r, r, L, 1.f, Q, L, Q, L, 0.f, sh.G, r, 0, P, sh.gws, sh.gws_bytes, stream);
   if (rc) return rc;
@@ -962,9 +990,6 @@ static int svd_precondition(const float* A, int64_t lda, int trans, int r, int L
   return check_cuda(cudaGetLastError(), "svd precondition");
 }
 
-// ---------------------------------------------------------------------------
-// host side
-// ---------------------------------------------------------------------------
 struct SvdPlan {
   int64_t m, n;        // A is m x n
   int trans;           // 1 when m > n (work on A^T)
@@ -1029,11 +1054,22 @@ static bool pre_enabled() {
   return v != 0;
 }
 
-// worth it when the rows shrink by a quarter or more (L + r -> 2 r) and the matrix is large enough for the
-// tensor-core phase to dominate
+// Worth it whenever the tensor-core phase dominates (r >= 512): wide matrices get rows of length 2 r instead of
+// L + r, and every matrix gets fewer sweeps -- the Jacobi phase works on the rows of Lm^T, the triangular factor of the
+// OTHER Gram (one step of the Cholesky-LR iteration towards the diagonal): 13 -> 10 sweeps at n = 2048 in the numpy
+// prototype, where the rows of Lm itself (same Gram as Y0) need the 13 of the plain route.
+// GRASP_SVD_PRECOND_SQUARE=0 restricts it to L >= 1.5 r, GRASP_SVD_PRECOND_T=0 factors Lm instead of Lm^T.
 static bool pre_eligible(int64_t m, int64_t n) {
+  static int sq = -1;
+  if (sq < 0) { const char* e = getenv("GRASP_SVD_PRECOND_SQUARE"); sq = e ? atoi(e) : 1; }
   const int64_t r = m < n ? m : n, L = m < n ? n : m;
-  return r >= 512 && 2 * L >= 3 * r;
+  return r >= 512 && (sq || 2 * L >= 3 * r);
+}
+
+static bool pre_transposed() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GRASP_SVD_PRECOND_T"); v = e ? atoi(e) : 1; }
+  return v != 0;
 }
 
 static SvdPlan make_plan(int64_t m, int64_t n, bool allow_pre) {
@@ -1041,6 +1077,7 @@ static SvdPlan make_plan(int64_t m, int64_t n, bool allow_pre) {
   const int64_t r = m < n ? m : n, L = m < n ? n : m;
   SvdPlan P = make_plan_plain(r, r);
   P.pre = 1; P.trans0 = (m > n); P.m0 = m; P.n0 = n; P.L0 = L;
+  P.trans = pre_transposed() ? 1 : 0;        // the Jacobi phase factors Y0' = Lm^T (or Lm)
   size_t o = P.bytes;
   P.off_Lm = o;      o = align_up(o + (size_t)r * r * 4, 1024);
   P.off_Q = o;       o = align_up(o + (size_t)r * L * 4, 1024);
@@ -1389,26 +1426,33 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
       rc = grasp_topk_batched(1, &sc, &rr, &kk, &perm, stream);
       if (rc) break;
       if (Q.pre) {
-        // Lm = Usq S Wt (Wt = normalised rows of Y, Usq = QT^T) and Y0 = Lm Qb:  Y0 = Usq S (Wt Qb)
+        // The Jacobi phase factored Y0' = Usq S Wt (Wt = normalised rows of Y, Usq = QT^T) with Y0' = Lm or Lm^T,
+        // and Y0 = Lm Qb.  Let (Ul, Vlt) be the factors of Lm = Ul S Vlt: (Usq, Wt) or (Wt^T, Usq^T).  Then
+        //   A = Y0   (trans0 = 0):  U = Ul,           Vh = Vlt Qb
+        //   A = Y0^T (trans0 = 1):  U = Qb^T Vlt^T,   Vh = Ul^T
         const int r = Q.r;
         const int64_t L0 = Q.L0;
-        float* Wt = sh.G;                                             // [r][r], free since the preconditioning
+        float* Wb = sh.G;                                             // [r][r] scratch, free since the preconditioning
         const float* Qb = reinterpret_cast<const float*>(base[i] + Q.off_Q);
+        const int lt = Q.trans;                                       // 1: Y0' = Lm^T
+        // rows of Vlt: normalised rows of Y (lt = 0) or rows of QT (lt = 1)
+        const int vl_col0 = lt ? Q.Lp : 0, vl_norm = lt ? 0 : 1;
+        // Ul: QT^T (lt = 0) or the normalised rows of Y transposed (lt = 1)
+        const int ul_col0 = lt ? 0 : Q.Lp, ul_norm = lt ? 1 : 0;
         if (!Q.trans0) {
-          // A = Y0:  U = Usq,  Vh = Wt Qb
-          GRASP_LAUNCH(svd_emit_rows_kernel, dim3(r), dim3(256), 0, st, g.mat[j].Z, Q.ldz, 0, perm, sigma, 1, r, r, Wt,
-                       (int64_t)r, S[i]);
+          GRASP_LAUNCH(svd_emit_rows_kernel, dim3(r), dim3(256), 0, st, g.mat[j].Z, Q.ldz, vl_col0, perm, sigma, vl_norm, r, r,
+                       Wb, (int64_t)r, S[i]);
           GRASP_LAUNCH(svd_emit_cols_kernel, dim3((r + 31) / 32, (unsigned)((r + 31) / 32)), dim3(32, 8), 0, st,
-                       g.mat[j].Z, Q.ldz, Q.Lp, perm, sigma, 0, r, r, U[i], (int64_t)r);
-          rc = tc_gemm_f32(0, 0, r, L0, r, 1.f, Wt, r, Qb, L0, 0.f, Vh[i], Q.n0, 0, GRASP_PREC_F16X3, sh.gws, sh.gws_bytes,
+                       g.mat[j].Z, Q.ldz, ul_col0, perm, sigma, ul_norm, r, r, U[i], (int64_t)r);
+          rc = tc_gemm_f32(0, 0, r, L0, r, 1.f, Wb, r, Qb, L0, 0.f, Vh[i], Q.n0, 0, GRASP_PREC_F16X3, sh.gws, sh.gws_bytes,
                            stream);
         } else {
-          // A = Y0^T = (Wt Qb)^T S Usq^T:  U = Qb^T Wt^T,  Vh = Usq^T = rows of QT
-          GRASP_LAUNCH(svd_emit_rows_kernel, dim3(r), dim3(256), 0, st, g.mat[j].Z, Q.ldz, 0, perm, sigma, 1, r, r, Wt,
-                       (int64_t)r, (float*)nullptr);
-          GRASP_LAUNCH(svd_emit_rows_kernel, dim3(r), dim3(256), 0, st, g.mat[j].Z, Q.ldz, Q.Lp, perm, sigma, 0, r, r,
+          GRASP_LAUNCH(svd_emit_rows_kernel, dim3(r), dim3(256), 0, st, g.mat[j].Z, Q.ldz, vl_col0, perm, sigma, vl_norm, r, r,
+                       Wb, (int64_t)r, (float*)nullptr);
+          // Vh = Ul^T: row i of Vh is column i of Ul = (sorted) row i of QT (lt = 0) / normalised row i of Y (lt = 1)
+          GRASP_LAUNCH(svd_emit_rows_kernel, dim3(r), dim3(256), 0, st, g.mat[j].Z, Q.ldz, ul_col0, perm, sigma, ul_norm, r, r,
                        Vh[i], (int64_t)Q.n0, S[i]);
-          rc = tc_gemm_f32(1, 1, L0, r, r, 1.f, Qb, L0, Wt, r, 0.f, U[i], r, 0, GRASP_PREC_F16X3, sh.gws, sh.gws_bytes,
+          rc = tc_gemm_f32(1, 1, L0, r, r, 1.f, Qb, L0, Wb, r, 0.f, U[i], r, 0, GRASP_PREC_F16X3, sh.gws, sh.gws_bytes,
                            stream);
         }
         if (rc) break;
