@@ -1054,14 +1054,16 @@ static bool pre_enabled() {
   return v != 0;
 }
 
-// Worth it whenever the tensor-core phase dominates (r >= 512): wide matrices get rows of length 2 r instead of
-// L + r, and every matrix gets fewer sweeps -- the Jacobi phase works on the rows of Lm^T, the triangular factor of the
-// OTHER Gram (one step of the Cholesky-LR iteration towards the diagonal): 13 -> 10 sweeps at n = 2048 in the numpy
-// prototype, where the rows of Lm itself (same Gram as Y0) need the 13 of the plain route.
-// GRASP_SVD_PRECOND_SQUARE=0 restricts it to L >= 1.5 r, GRASP_SVD_PRECOND_T=0 factors Lm instead of Lm^T.
+// Worth it when the rows shrink by a quarter or more (L + r -> 2 r) and the matrix is large enough for the tensor-core
+// phase to dominate.  The Jacobi phase works on the rows of Lm^T, the triangular factor of the OTHER Gram (one step of
+// the Cholesky-LR iteration towards the diagonal), which also saves sweeps: 17 -> 14 at 4096 x 4096, 16 -> 15 at
+// 4096 x 11008 on the B200 (profiles/r02_svd_times_precond_v2.txt), where the rows of Lm itself (same Gram as Y0) need
+// as many as the plain route.  For square matrices those three sweeps (~40 ms) just pay for the three Cholesky passes
+// (~35 ms, launch-bound recursion), so they take the plain route unless GRASP_SVD_PRECOND_SQUARE=1.
+// GRASP_SVD_PRECOND_T=0 factors Lm instead of Lm^T.
 static bool pre_eligible(int64_t m, int64_t n) {
   static int sq = -1;
-  if (sq < 0) { const char* e = getenv("GRASP_SVD_PRECOND_SQUARE"); sq = e ? atoi(e) : 1; }
+  if (sq < 0) { const char* e = getenv("GRASP_SVD_PRECOND_SQUARE"); sq = e ? atoi(e) : 0; }
   const int64_t r = m < n ? m : n, L = m < n ? n : m;
   return r >= 512 && (sq || 2 * L >= 3 * r);
 }

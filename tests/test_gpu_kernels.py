@@ -158,23 +158,35 @@ def test_svd_preconditioned_wide_and_tall(cuda, m, n):
     assert ((outs[0][1] - S2).abs().max() / S2[0]).item() < 2e-6
 
 
-def test_svd_preconditioning_flags_ill_conditioned_input_and_the_engine_recovers(cuda):
-    """cond(A) = 1e6: cond(A A^T) is beyond fp32, the Cholesky factorisation breaks down.  The call reports it in
-    info[1] (never silently wrong factors) and engine.batched_svd factors the matrix again without preconditioning."""
-    from grasp_b200 import engine, ops
-    g = torch.Generator().manual_seed(5)
-    r, L = 512, 1536
+def _graded(r, L, decades, seed):
+    g = torch.Generator().manual_seed(seed)
     Uo, _ = torch.linalg.qr(torch.randn(r, r, generator=g, dtype=torch.float64))
     Vo, _ = torch.linalg.qr(torch.randn(L, r, generator=g, dtype=torch.float64))
-    sv = torch.logspace(0, -6, r, dtype=torch.float64)
-    A = ((Uo * sv) @ Vo.T).float()
-    _, info = ops.svd_batched([A.to(cuda)], return_info=True)
+    sv = torch.logspace(0, -decades, r, dtype=torch.float64)
+    return ((Uo * sv) @ Vo.T).float()
+
+
+def test_svd_preconditioning_on_ill_conditioned_input(cuda):
+    """cond(A) = 1e6: the shifted first Cholesky pass keeps the preconditioning sound (cond(A A^T) is beyond fp32).
+    cond(A) = 1e10: it cannot be; the call reports that in info[1] (never silently wrong factors) and
+    engine.batched_svd factors the matrix again without preconditioning."""
+    from grasp_b200 import engine, ops
+
+    def check(A, U, S, Vh):
+        A64, S64 = A.double(), torch.linalg.svdvals(A.double())
+        assert ((S.double().cpu() - S64).abs().max() / S64[0]).item() < 1e-5
+        rec = (torch.linalg.norm((U.double().cpu() * S.double().cpu()) @ Vh.double().cpu() - A64) / torch.linalg.norm(A64)).item()
+        assert rec < 1e-5, rec
+
+    A6 = _graded(512, 1536, 6, 5)
+    (usv,), info = ops.svd_batched([A6.to(cuda)], return_info=True)
+    if int(info.cpu()[0, 1]):                         # reported sound -> it must be accurate
+        check(A6, *usv)
+    check(A6, *engine.batched_svd([A6.to(cuda)])[0])
+    A10 = _graded(512, 1536, 10, 6)
+    _, info = ops.svd_batched([A10.to(cuda)], return_info=True)
     assert int(info.cpu()[0, 1]) == 0, "an unsound preconditioning must be reported"
-    (U, S, Vh), = engine.batched_svd([A.to(cuda)])
-    A64, S64 = A.double(), torch.linalg.svdvals(A.double())
-    assert ((S.double().cpu() - S64).abs().max() / S64[0]).item() < 1e-5
-    rec = (torch.linalg.norm((U.double().cpu() * S.double().cpu()) @ Vh.double().cpu() - A64) / torch.linalg.norm(A64)).item()
-    assert rec < 1e-5, rec
+    check(A10, *engine.batched_svd([A10.to(cuda)])[0])
 
 
 def test_svd_batched_mixed_shapes_and_info(cuda):
