@@ -52,6 +52,21 @@ elif what == "svd4":
     # one batch of four 4096 x 4096 matrices, two sweeps (what the 7B job's attention projections look like)
     As = [torch.randn(4096, 4096, device=dev) * 0.02 for _ in range(4)]
     ops.svd_batched(As, max_sweeps=1)
+elif what == "svd8":
+    # the job's batches: eight 4096 x 4096 matrices (attention projections of two layers), one sweep
+    As = [torch.randn(4096, 4096, device=dev) * 0.02 for _ in range(8)]
+    ops.svd_batched(As, max_sweeps=1)
+elif what == "attn":
+    import math
+    from grasp_b200 import _lib
+    B, S, H, D = 16, 511, 32, 128
+    q = torch.randn(B * S, H * D, device=dev); k = torch.randn(B * S, H * D, device=dev); v = torch.randn(B * S, H * D, device=dev)
+    do = torch.randn(B * S, H * D, device=dev) * 1e-3
+    cos = torch.randn(1, S, D, device=dev); sin = torch.randn(1, S, D, device=dev)
+    for _ in range(2):
+        qo, ko, vo = ops.attn_prep_qkv(q, k, v, S, H, H, D, cos, sin)
+        out, ctx = ops.attn_fwd_prepared(qo, ko, vo, B, S, H, H, D, 1 / math.sqrt(D))
+        ops.attn_bwd(ctx, do)
 elif what == "svd":
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
     A = torch.randn(n, n, device=dev) * 0.02

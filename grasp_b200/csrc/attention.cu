@@ -9,10 +9,11 @@
 // GRASP_SCALE_TENSOR on the [tokens, heads * head_dim] activations, so one tile in shared memory serves as a
 // K-major operand (contracted over head_dim) and as an MN-major operand (contracted over tokens).
 //
-// Forward, one CTA per (batch, head, 128 queries), 192 threads:
+// Forward, one CTA per (batch, head, 128 queries), 320 threads:
 //   warp 0    TMA producer: the Q tile once, then (K_j, V_j) tiles of 64 keys through a two-stage ring
 //   warp 1    MMA issuer:   S_j = Q K_j^T (128 x 64, TMEM);  O_j = P_j V_j (128 x D, TMEM)
-//   warps 2-5 softmax:      one query row per thread (= TMEM lane): S_j -> online max / sum -> P_j as fp16 planes
+//   warps 2-9 softmax:      two threads per query row (= TMEM lane), 32 score columns each: S_j -> online max / sum
+//                           (row maximum exchanged through shared memory) -> P_j as fp16 planes
 //                           (x 2^14) in the K-major swizzled layout the MMA reads; O_j is drained into fp32
 //                           registers, O = O * corr + O_j (round-to-nearest adds, no truncating TMEM chain)
 // Keys beyond the causal diagonal are masked, so tiles right of the diagonal are never loaded; rows past the end
@@ -28,7 +29,10 @@ using namespace tc;
 
 constexpr int AT_BQ = 128;        // queries per CTA = TMEM lanes
 constexpr int AT_BK = 64;         // keys per step
-constexpr int AT_THREADS = 192;
+constexpr int AT_SM_WARPS = 8;    // softmax / epilogue warps: two per TMEM lane quadrant, each half of the columns
+constexpr int AT_SM_THREADS = 32 * AT_SM_WARPS;
+constexpr int AT_THREADS = 64 + AT_SM_THREADS;   // + TMA warp + MMA warp
+constexpr int AT_HC = AT_BK / 2;   // score columns per softmax thread
 constexpr float AT_P_SCALE = 16384.f;          // probabilities (<= 1) as fp16 planes: p * 2^14 = hi + lo
 constexpr float AT_P_INV = 1.f / 16384.f;
 
@@ -54,13 +58,15 @@ __device__ __forceinline__ void at_split8(const float* v, uint4& hi, uint4& lo) 
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// 64 fp32 values of this thread's row -> (hi, lo) fp16 planes of a [128][64] K-major tile with the 128-byte
+// 32 fp32 values of this thread's half row -> (hi, lo) fp16 planes of a [128][64] K-major tile with the 128-byte
 // swizzle (16-byte chunk c8 of row r sits at c8 ^ (r & 7))
-__device__ __forceinline__ void at_store_planes(unsigned char* T, int plane_bytes, int row, const float* v) {
+// (this thread writes the 32 columns [32 * half, 32 * half + 32) of its row: chunks 4 * half .. 4 * half + 3)
+__device__ __forceinline__ void at_store_planes(unsigned char* T, int plane_bytes, int row, int half, const float* v) {
 #pragma unroll
-  for (int c8 = 0; c8 < 8; ++c8) {
+  for (int c = 0; c < 4; ++c) {
+    const int c8 = half * 4 + c;
     uint4 hi, lo;
-    at_split8(v + c8 * 8, hi, lo);
+    at_split8(v + c * 8, hi, lo);
     const int off = row * 128 + ((c8 ^ (row & 7)) << 4);
     *reinterpret_cast<uint4*>(T + off) = hi;
     *reinterpret_cast<uint4*>(T + plane_bytes + off) = lo;
@@ -106,6 +112,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
   unsigned char* Ps = smem + Cfg::OFF_P;
   __shared__ uint64_t q_full, kv_full[Cfg::STAGES], kv_empty[Cfg::STAGES], s_full, p_full, o_full;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float xch[2][AT_BQ];        // [column half][row]: partial row maxima, then partial sums (1 KB: 224 KB + barriers fill the CTA's shared memory)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nqt = (p.S + AT_BQ - 1) / AT_BQ;
@@ -121,7 +128,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
     prefetch_tmap(&mapQ); prefetch_tmap(&mapK); prefetch_tmap(&mapV);
     mbar_init(&q_full, 1);
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    mbar_init(&s_full, 1); mbar_init(&o_full, 1); mbar_init(&p_full, 128);
+    mbar_init(&s_full, 1); mbar_init(&o_full, 1); mbar_init(&p_full, AT_SM_THREADS);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(&tmem_base_smem);
@@ -201,42 +208,46 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
       }
     }
   } else {
-    // ---------------------------------------------------------------- softmax + output (warps 2..5)
+    // ---------------------------------------------------------------- softmax + output (warps 2..9)
+    constexpr int DH = D / 2;                          // output columns per thread
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;                  // which 32 score columns / which half of the head dimension
     const int row = quad * 32 + lane;                  // row of the tile = TMEM lane
     const int qi = q0 + row;                           // query position in the sequence
-    const uint32_t t_s = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const uint32_t t_o = t_s + 64;
+    const uint32_t t_s = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * AT_HC);
+    const uint32_t t_o = tmem_base + ((uint32_t)(quad * 32) << 16) + 64 + (uint32_t)(half * DH);
     const float c1 = p.inv_q[0] * p.inv_k[0] * p.scale_log2;
     const float c2 = p.inv_v[0] * AT_P_INV;
-    float m = -INFINITY, l = 0.f;
-    float oacc[D];
+    float m = -INFINITY, l = 0.f;                      // l: this thread's share of the row sum
+    float oacc[DH];
 #pragma unroll
-    for (int i = 0; i < D; ++i) oacc[i] = 0.f;
+    for (int i = 0; i < DH; ++i) oacc[i] = 0.f;
     for (int j = 0; j < nk; ++j) {
       mbar_wait(&s_full, j & 1);
       tc_fence_after_sync();
-      float s[64];
+      float s[AT_HC];
       tmem_ld_32x32(t_s, s);
-      tmem_ld_32x32(t_s + 32, s + 32);
       tmem_ld_wait();
-      const int key0 = j * AT_BK;
+      const int key0 = j * AT_BK + half * AT_HC;
       float mx = -INFINITY;
-      if (key0 + AT_BK - 1 <= q0) {                      // tile entirely left of the diagonal: nothing to mask
+      if (j * AT_BK + AT_BK - 1 <= q0) {                 // tile entirely left of the diagonal: nothing to mask
 #pragma unroll
-        for (int c = 0; c < 64; ++c) { s[c] *= c1; mx = fmaxf(mx, s[c]); }
+        for (int c = 0; c < AT_HC; ++c) { s[c] *= c1; mx = fmaxf(mx, s[c]); }
       } else {
 #pragma unroll
-        for (int c = 0; c < 64; ++c) {
+        for (int c = 0; c < AT_HC; ++c) {
           s[c] = (key0 + c <= qi) ? s[c] * c1 : -INFINITY;
           mx = fmaxf(mx, s[c]);
         }
       }
-      const float m_new = fmaxf(m, mx);                // finite from the first tile on (key 0 is always visible)
+      xch[half][row] = mx;
+      asm volatile("bar.sync 1, %0;" ::"n"(AT_SM_THREADS) : "memory");
+      const float m_new = fmaxf(m, fmaxf(mx, xch[half ^ 1][row]));   // finite from the first tile on
+      asm volatile("bar.sync 1, %0;" ::"n"(AT_SM_THREADS) : "memory");   // (the slot is rewritten in the next step)
       const float corr = at_exp2(m - m_new);
       float lsum = 0.f;
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
+      for (int c = 0; c < AT_HC; ++c) {
         const float e = at_exp2(s[c] - m_new);
         lsum += e;
         s[c] = e * AT_P_SCALE;
@@ -244,7 +255,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
       l = l * corr + lsum;
       m = m_new;
       // P_j (x 2^14) as fp16 planes in the layout the MMA reads
-      at_store_planes(Ps, Cfg::P_PLANE, row, s);
+      at_store_planes(Ps, Cfg::P_PLANE, row, half, s);
       fence_proxy_async();
       tc_fence_before_sync();
       mbar_arrive(&p_full);
@@ -252,7 +263,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
       mbar_wait(&o_full, j & 1);
       tc_fence_after_sync();
 #pragma unroll
-      for (int c = 0; c < D / 32; ++c) {
+      for (int c = 0; c < DH / 32; ++c) {
         float t[32];
         tmem_ld_32x32(t_o + (uint32_t)(c * 32), t);
         tmem_ld_wait();
@@ -261,14 +272,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
       }
       tc_fence_before_sync();
     }
-    // ---- normalise and store (P's shared memory is free now: staging tile of 32 x 32 floats per warp)
+    // ---- row sum = the two halves' shares; normalise and store (P's shared memory is free now: one 32 x 32 float
+    //      staging tile per warp)
+    xch[half][row] = l;
+    asm volatile("bar.sync 1, %0;" ::"n"(AT_SM_THREADS) : "memory");
+    l += xch[half ^ 1][row];
     const float inv_l = 1.f / l;
-    if (qi < p.S) p.lse2[((int64_t)b * p.H + h) * p.S + qi] = m + log2f(l);
+    if (half == 0 && qi < p.S) p.lse2[((int64_t)b * p.H + h) * p.S + qi] = m + log2f(l);
     float* stg = reinterpret_cast<float*>(Ps) + (warp - 2) * 1024;
     const int sub = lane >> 3, pos = lane & 7;
     const int row_base = q0 + quad * 32;
 #pragma unroll
-    for (int c = 0; c < D / 32; ++c) {
+    for (int c = 0; c < DH / 32; ++c) {
 #pragma unroll
       for (int q = 0; q < 8; ++q)
         *reinterpret_cast<float4*>(stg + lane * 32 + ((q ^ (lane & 7)) << 2)) =
@@ -278,7 +293,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = i * 4 + sub;
-        const int col = c * 32 + ((pos ^ (r & 7)) << 2);
+        const int col = half * DH + c * 32 + ((pos ^ (r & 7)) << 2);
         const float4 o = *reinterpret_cast<const float4*>(stg + r * 32 + (pos << 2));
         if (row_base + r < p.S)
           *reinterpret_cast<float4*>(p.out + (int64_t)(tok0 + row_base + r) * p.ld_out + h * D + col) = o;
@@ -337,14 +352,15 @@ struct AtBwdCfg {
   static constexpr float KAPPA = (D == 128) ? 5.9604644775390625e-8f /*2^-24*/ : 1.1920928955078125e-7f /*2^-23*/;
 };
 
-// drain a [128 lanes x D] fp32 accumulator from TMEM, scale it and store rows [row0, row0 + 128) x [col0, col0 + D)
-// of a row-major matrix; rows >= row_limit are skipped.  stg: this warp's 32 x 32 float staging tile.
-template <int D>
+// drain NC columns of a [128 lanes x .] fp32 accumulator from TMEM (taddr = first of them), scale and store them to
+// rows [row_first, row_first + 128) x [col0, col0 + NC) of a row-major matrix; rows >= rows_valid are skipped.
+// stg: this warp's 32 x 32 float staging tile.
+template <int NC>
 __device__ __forceinline__ void at_drain_store(uint32_t taddr, float factor, float* stg, float* dst, int64_t ld,
                                                int64_t row_first, int rows_valid, int col0, int quad, int lane) {
   const int sub = lane >> 3, pos = lane & 7;
 #pragma unroll
-  for (int c = 0; c < D / 32; ++c) {
+  for (int c = 0; c < NC / 32; ++c) {
     float t[32];
     tmem_ld_32x32(taddr + (uint32_t)(c * 32), t);
     tmem_ld_wait();
@@ -393,7 +409,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapQ); prefetch_tmap(&mapDO); prefetch_tmap(&mapK); prefetch_tmap(&mapV);
     mbar_init(&a_full, 1); mbar_init(&kv_full, 1); mbar_init(&kv_empty, 1);
-    mbar_init(&s_full, 1); mbar_init(&t_full, 128);
+    mbar_init(&s_full, 1); mbar_init(&t_full, AT_SM_THREADS);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<256>(&tmem_base_smem);
@@ -469,7 +485,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       umma_commit(&s_full);                              // (nk-th phase) everything issued has completed
     }
   } else {
+    constexpr int DH = D / 2;
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;                  // 32 of the 64 keys of a step; half of the head dimension at the end
     const int row = quad * 32 + lane;
     const int qi = q0 + row;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
@@ -481,25 +499,18 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     for (int j = 0; j < nk; ++j) {
       mbar_wait(&s_full, j & 1);
       tc_fence_after_sync();
-      float s[64], dp[32];
-      tmem_ld_32x32(t_lane, s);
-      tmem_ld_32x32(t_lane + 32, s + 32);
+      float s[AT_HC], dp[AT_HC];
+      tmem_ld_32x32(t_lane + (uint32_t)(half * AT_HC), s);
+      tmem_ld_32x32(t_lane + 64 + (uint32_t)(half * AT_HC), dp);
       tmem_ld_wait();
-      const int key0 = j * AT_BK;
+      const int key0 = j * AT_BK + half * AT_HC;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        tmem_ld_32x32(t_lane + 64 + (uint32_t)(half * 32), dp);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const int cc = half * 32 + c;
-          const float pr = (live && key0 + cc <= qi) ? at_exp2(s[cc] * c1 - lse) : 0.f;
-          s[cc] = pr * (dp[c] - del_raw) * Cfg::KAPPA;
-        }
+      for (int c = 0; c < AT_HC; ++c) {
+        const float pr = (live && key0 + c <= qi) ? at_exp2(s[c] * c1 - lse) : 0.f;
+        s[c] = pr * (dp[c] - del_raw) * Cfg::KAPPA;
       }
-      // the dS tile of the previous step was released by kv_empty ... which the producer consumed; the MMA of the
-      // previous step completed before s_full of this step (same commit order), so Ts is free here
-      at_store_planes(Ts, Cfg::T_PLANE, row, s);
+      // Ts is free here: the dQ product of the previous step completed before s_full of this step (same commit order)
+      at_store_planes(Ts, Cfg::T_PLANE, row, half, s);
       fence_proxy_async();
       tc_fence_before_sync();
       mbar_arrive(&t_full);
@@ -509,7 +520,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     tc_fence_after_sync();
     const float c_dq = p.scale * idv * p.inv_k[0] / Cfg::KAPPA;
     float* stg = reinterpret_cast<float*>(Ts) + (warp - 2) * 1024;
-    at_drain_store<D>(t_lane + 128, c_dq, stg, p.dq, (int64_t)p.H * D, (int64_t)tok0 + q0, p.S - q0, h * D, quad, lane);
+    at_drain_store<DH>(t_lane + 128 + (uint32_t)(half * DH), c_dq, stg, p.dq, (int64_t)p.H * D, (int64_t)tok0 + q0, p.S - q0,
+                       h * D + half * DH, quad, lane);
   }
 
   tc_fence_before_sync();
@@ -554,7 +566,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapK); prefetch_tmap(&mapV); prefetch_tmap(&mapQ); prefetch_tmap(&mapDO);
     mbar_init(&a_full, 1); mbar_init(&qd_full, 1); mbar_init(&qd_empty, 1);
-    mbar_init(&s_full, 1); mbar_init(&dv_done, 1); mbar_init(&pt_full, 128); mbar_init(&dst_full, 128);
+    mbar_init(&s_full, 1); mbar_init(&dv_done, 1); mbar_init(&pt_full, AT_SM_THREADS); mbar_init(&dst_full, AT_SM_THREADS);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(&tmem_base_smem);
@@ -643,10 +655,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
       umma_commit(&s_full);                              // phase nsteps: all accumulations have completed
     }
   } else {
+    constexpr int DH = D / 2;
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;                    // 32 of the 64 queries of a step; half of the head dimension at the end
     const int row = quad * 32 + lane;
     const int key = k0 + row;
-    const int stid = threadIdx.x - 64;                   // 0..127
+    const int stid = threadIdx.x - 64;                   // 0..255
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
     const float c1 = p.inv_q[0] * p.inv_k[0] * p.scale_log2;
     const float idv = p.inv_do[0] * p.inv_v[0];
@@ -654,47 +668,40 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
       const int h = hk * group + t / steps_per_head;
       const int i = i_first + t % steps_per_head;
       // lse2 / delta of the 64 queries of this step (columns of the transposed tiles)
-      {
+      if (stid < 128) {
         const int c = stid & 63;
         const int qi = i * 64 + c;
         const float v = (qi < p.S) ? (stid < 64 ? p.lse2 : p.delta)[((int64_t)b * p.H + h) * p.S + qi] : 0.f;
         if (stid < 64) col_lse[t & 1][c] = v; else col_del[t & 1][c] = v / idv;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(AT_SM_THREADS) : "memory");
       mbar_wait(&s_full, t & 1);
       tc_fence_after_sync();
-      float s[64], dp[32];
-      tmem_ld_32x32(t_lane, s);
-      tmem_ld_32x32(t_lane + 32, s + 32);
+      float s[AT_HC], dp[AT_HC];
+      tmem_ld_32x32(t_lane + (uint32_t)(half * AT_HC), s);
+      tmem_ld_32x32(t_lane + 64 + (uint32_t)(half * AT_HC), dp);
       tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        const int qi = i * 64 + c;
-        s[c] = (qi < p.S && key <= qi && key < p.S) ? at_exp2(s[c] * c1 - col_lse[t & 1][c]) : 0.f;   // P^T
+      for (int c = 0; c < AT_HC; ++c) {
+        const int cc = half * AT_HC + c;
+        const int qi = i * 64 + cc;
+        s[c] = (qi < p.S && key <= qi && key < p.S) ? at_exp2(s[c] * c1 - col_lse[t & 1][cc]) : 0.f;   // P^T
       }
       // the buffer's previous content (dS^T of step t-1) was consumed: qd_empty(t-1) preceded qd_full(t) <= s_full(t)
       {
-        float ps[64];
+        float ps[AT_HC];
 #pragma unroll
-        for (int c = 0; c < 64; ++c) ps[c] = s[c] * AT_P_SCALE;
-        at_store_planes(Ts, Cfg::T_PLANE, row, ps);
+        for (int c = 0; c < AT_HC; ++c) ps[c] = s[c] * AT_P_SCALE;
+        at_store_planes(Ts, Cfg::T_PLANE, row, half, ps);
       }
       fence_proxy_async();
       tc_fence_before_sync();
       mbar_arrive(&pt_full);
       // dS^T = P^T o (dP^T - delta)
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        tmem_ld_32x32(t_lane + 64 + (uint32_t)(half * 32), dp);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const int cc = half * 32 + c;
-          s[cc] = s[cc] * (dp[c] - col_del[t & 1][cc]) * Cfg::KAPPA;
-        }
-      }
+      for (int c = 0; c < AT_HC; ++c) s[c] = s[c] * (dp[c] - col_del[t & 1][half * AT_HC + c]) * Cfg::KAPPA;
       mbar_wait(&dv_done, t & 1);                        // the dV product has finished reading P^T
-      at_store_planes(Ts, Cfg::T_PLANE, row, s);
+      at_store_planes(Ts, Cfg::T_PLANE, row, half, s);
       fence_proxy_async();
       tc_fence_before_sync();
       mbar_arrive(&dst_full);
@@ -704,8 +711,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_const
     const float c_dv = p.inv_do[0] * AT_P_INV;
     const float c_dk = p.scale * idv * p.inv_q[0] / Cfg::KAPPA;
     float* stg = reinterpret_cast<float*>(Ts) + (warp - 2) * 1024;
-    at_drain_store<D>(t_lane + 128, c_dv, stg, p.dv, (int64_t)p.Hkv * D, (int64_t)tok0 + k0, p.S - k0, hk * D, quad, lane);
-    at_drain_store<D>(t_lane + 128 + D, c_dk, stg, p.dk, (int64_t)p.Hkv * D, (int64_t)tok0 + k0, p.S - k0, hk * D, quad, lane);
+    at_drain_store<DH>(t_lane + 128 + (uint32_t)(half * DH), c_dv, stg, p.dv, (int64_t)p.Hkv * D, (int64_t)tok0 + k0, p.S - k0,
+                       hk * D + half * DH, quad, lane);
+    at_drain_store<DH>(t_lane + 128 + D + (uint32_t)(half * DH), c_dk, stg, p.dk, (int64_t)p.Hkv * D, (int64_t)tok0 + k0,
+                       p.S - k0, hk * D + half * DH, quad, lane);
   }
 
   tc_fence_before_sync();

@@ -69,6 +69,8 @@ def _worker(rank, world, port, out_dir):
         for i, (U, S, Vh) in enumerate(got):
             assert U.shape == (shapes[i][0], min(shapes[i])) and Vh.shape == (min(shapes[i]), shapes[i][1])
             assert torch.all(U == i) and torch.all(S == i) and torch.all(Vh == i)
+        # plans that decide how many collectives follow (SVD hoisting window) must agree on every rank
+        assert dist.all_min_int(5 + 3 * rank, "cpu") == 5
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         td.destroy_process_group()
