@@ -1180,6 +1180,9 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
       rc = check_cuda(cudaFuncSetAttribute(jacobi_tc_kernel<JT_GRAM3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            JtCfg<JT_GRAM3>::SMEM_BYTES), "jacobi_tc gram3 attr");
       if (rc) return rc;
+      rc = check_cuda(cudaFuncSetAttribute(jacobi_tc_kernel<JT_UPDATE2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           JtCfg<JT_UPDATE2>::SMEM_BYTES), "jacobi_tc update2 attr");
+      if (rc) return rc;
       tc_attr = true;
     }
   }
@@ -1294,7 +1297,24 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
     if (g.p >= 2) {
       const int tc_grid_g = min(sm_count(), g.nmat * P.ntiles * g.nsplit);
       const int tc_grid_u = min(sm_count(), g.nmat * P.ntiles * (g.ldz / 128));
+      // two-plane updates in the first sweeps (cyclic Jacobi needs ~log2(blocks) + 8 sweeps; the first log2(blocks) - 1
+      // are far from convergence).  GRASP_SVD_2PLANE_SWEEPS overrides (0 = three planes throughout, round 1).
+      int two_plane_sweeps = 0;
+      if (use_tc) {
+        for (int q = g.p; q > 2; q >>= 1) ++two_plane_sweeps;
+        if (two_plane_sweeps > 6) two_plane_sweeps = 6;
+        if (const char* e = getenv("GRASP_SVD_2PLANE_SWEEPS")) two_plane_sweeps = atoi(e);
+      }
       for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+        if (use_tc && sweep == two_plane_sweeps && two_plane_sweeps > 0) {
+          // the third plane was not maintained: from here on Z = p0 + p1 exactly
+          for (int j = 0; j < g.nmat && !rc; ++j) {
+            const SvdPlan& Q = plans[members[j]];
+            const size_t plane_bytes = (size_t)Q.rp * Q.ldz * 2;
+            rc = check_cuda(cudaMemsetAsync(base[members[j]] + Q.off_Zp + 2 * plane_bytes, 0, plane_bytes, st), "svd plane memset");
+          }
+          if (rc) break;
+        }
         for (int round = 0; round < g.p - 1; ++round) {
           if (use_tc) {
             jp.round = round;
@@ -1312,7 +1332,10 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
           else
             GRASP_LAUNCH(svd_evd_kernel<double>, dim3(g.npairs, g.nmat), dim3(EVD_THREADS), sizeof(EvdSmem<double>), st,
                          g, round, sweep, tol, inner_cap);
-          if (use_tc) {
+          if (use_tc && sweep < two_plane_sweeps) {
+            GRASP_LAUNCH(jacobi_tc_kernel<JT_UPDATE2>, dim3(tc_grid_u), dim3(JT_THREADS), JtCfg<JT_UPDATE2>::SMEM_BYTES,
+                         st, *maps, jp);
+          } else if (use_tc) {
             GRASP_LAUNCH(jacobi_tc_kernel<JT_UPDATE>, dim3(tc_grid_u), dim3(JT_THREADS), JtCfg<JT_UPDATE>::SMEM_BYTES,
                          st, *maps, jp);
           } else {
@@ -1322,6 +1345,7 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
         // tensor-core phase: stop once the Gram is diagonal to 1e-4 (its own drift is of that order anyway)
         GRASP_LAUNCH(svd_sweep_end_kernel, dim3(1), dim3(32), 0, st, g, sweep, use_tc ? 1e-4f : tol, -1);
       }
+      if (rc) { delete maps; break; }
       if (use_tc && no_cleanup_dbg) {
         for (int j = 0; j < g.nmat; ++j) {
           const SvdPlan& Q = plans[members[j]];

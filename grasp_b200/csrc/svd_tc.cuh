@@ -41,17 +41,23 @@ struct JtParams {
   int nmat, rp, Lp, ldz, p, npairs, ntiles, nsplit, round;
 };
 
-enum { JT_GRAM = 0, JT_UPDATE = 1, JT_GRAM3 = 2 };   // JT_GRAM3: all three planes / six products (clean-up sweeps)
+enum { JT_GRAM = 0, JT_UPDATE = 1, JT_GRAM3 = 2, JT_UPDATE2 = 3 };   // JT_GRAM3: all three planes / six products (clean-up
+                                                                    // sweeps); JT_UPDATE2: two planes / three products (early sweeps)
 
 template <int MODE>
 struct JtCfg {
   // the Gram only steers the rotations of a phase that stops at 1e-4: two planes / three products
   // (bf16x3, 4e-6) are plenty there; the update keeps all three planes (six products)
-  static constexpr bool IS_GRAM = (MODE != JT_UPDATE);
+  // JT_UPDATE2: while the off-diagonals are still large the third plane (bits 17..24) of Z and of the rotations buys
+  // nothing -- the clean-up stage recomputes Y = QT Y0 and re-orthogonalises QT anyway -- so the early sweeps read and
+  // write two planes: 8 instead of 12 bytes per element and round of the HBM-bound update.
+  static constexpr bool IS_GRAM = (MODE == JT_GRAM || MODE == JT_GRAM3);
+  static constexpr bool IS_UPDATE = !IS_GRAM;
   static constexpr int GRAM_PLANES = (MODE == JT_GRAM) ? 2 : 3;
-  static constexpr int STAGE_BYTES = (IS_GRAM ? GRAM_PLANES : 6) * JT_PLANE_TILE;
-  static constexpr int STAGES = (MODE == JT_GRAM) ? 6 : (MODE == JT_GRAM3 ? 4 : 2);
-  static constexpr int STORE_BYTES = (MODE == JT_UPDATE) ? 8 * 4096 : 0;   // one 32 x 64 bf16 staging tile per epilogue warp
+  static constexpr int UPD_PLANES = (MODE == JT_UPDATE2) ? 2 : 3;
+  static constexpr int STAGE_BYTES = (IS_GRAM ? GRAM_PLANES : 2 * UPD_PLANES) * JT_PLANE_TILE;
+  static constexpr int STAGES = (MODE == JT_GRAM) ? 6 : (MODE == JT_GRAM3 ? 4 : (MODE == JT_UPDATE2 ? 3 : 2));
+  static constexpr int STORE_BYTES = IS_UPDATE ? 8 * 4096 : 0;   // one 32 x 64 bf16 staging tile per epilogue warp
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_BYTES + 1024 + 256;
 };
 
@@ -105,7 +111,7 @@ jacobi_tc_kernel(const __grid_constant__ JtMaps maps, const JtParams p) {
       kb0 = 0; kb1 = 2;
     }
     if (p.mat[m].stats[0]) return false;                      // matrix already converged
-    if (MODE == JT_UPDATE) {
+    if (Cfg::IS_UPDATE) {
       const int f0 = p.mat[m].pair_flag[tile * 2];
       const int f1 = (tile * 2 + 1 < p.npairs) ? p.mat[m].pair_flag[tile * 2 + 1] : 0;
       if (!f0 && !f1) return false;                           // both rotations are the identity
@@ -134,9 +140,9 @@ jacobi_tc_kernel(const __grid_constant__ JtMaps maps, const JtParams p) {
               for (int c = 0; c < 4; ++c)
                 tma_load_4d(st + pl * JT_PLANE_TILE + c * 4096, zmap, &full_bar[stage], (kb & 1) * 64, rows[c], kb >> 1, pl);
           } else {
-            unsigned char* sB = st + 3 * JT_PLANE_TILE;
+            unsigned char* sB = st + Cfg::UPD_PLANES * JT_PLANE_TILE;
 #pragma unroll
-            for (int pl = 0; pl < 3; ++pl) {
+            for (int pl = 0; pl < Cfg::UPD_PLANES; ++pl) {
               // A: ET planes, 128 m x 64 k of K block kb
               tma_load_3d(st + pl * JT_PLANE_TILE, &maps.et[m], &full_bar[stage], kb * 64, tile * 128, pl);
               // B: rows of Z as K (two 32-row chunks per K block), 128 columns as two 64-wide halves
@@ -154,11 +160,12 @@ jacobi_tc_kernel(const __grid_constant__ JtMaps maps, const JtParams p) {
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0, MODE == JT_UPDATE ? 1 : 0);
-      // plane products, small terms first; the Gram uses planes {0,1} only: (1,0) (0,1) (0,0)
-      constexpr int NPROD = (MODE == JT_GRAM) ? 3 : 6;
-      constexpr int PA[6] = {MODE == JT_GRAM ? 1 : 2, 0, MODE == JT_GRAM ? 0 : 1, 1, 0, 0};
-      constexpr int PB[6] = {0, MODE == JT_GRAM ? 1 : 2, MODE == JT_GRAM ? 0 : 1, 0, 1, 0};
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0, Cfg::IS_UPDATE ? 1 : 0);
+      // plane products, small terms first; two-plane modes use planes {0,1} only: (1,0) (0,1) (0,0)
+      constexpr bool TWO = (MODE == JT_GRAM || MODE == JT_UPDATE2);
+      constexpr int NPROD = TWO ? 3 : 6;
+      constexpr int PA[6] = {TWO ? 1 : 2, 0, TWO ? 0 : 1, 1, 0, 0};
+      constexpr int PB[6] = {0, TWO ? 1 : 2, TWO ? 0 : 1, 0, 1, 0};
       constexpr bool IS_GRAM_ = Cfg::IS_GRAM;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -171,7 +178,7 @@ jacobi_tc_kernel(const __grid_constant__ JtMaps maps, const JtParams p) {
           tc_fence_after_sync();
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
           const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t sB = IS_GRAM_ ? sA : sA + 3 * JT_PLANE_TILE;
+          const uint32_t sB = IS_GRAM_ ? sA : sA + Cfg::UPD_PLANES * JT_PLANE_TILE;
 #pragma unroll
           for (int q = 0; q < NPROD; ++q) {
             const uint64_t da = umma_desc_kmajor_sw128(sA + PA[q] * JT_PLANE_TILE);
@@ -237,7 +244,7 @@ jacobi_tc_kernel(const __grid_constant__ JtMaps maps, const JtParams p) {
         unsigned char* stg = smem + STAGES * Cfg::STAGE_BYTES + (warp - 2) * 4096;
         const int row0 = jt_chunk_row(p, tile, quad);       // this warp's 32 rows are chunk `quad` of the tile
 #pragma unroll
-        for (int pl = 0; pl < 3; ++pl) {
+        for (int pl = 0; pl < Cfg::UPD_PLANES; ++pl) {
           if (lane == 0) tma_store_wait_read();              // the previous store has finished reading `stg`
           __syncwarp();
 #pragma unroll
@@ -270,7 +277,7 @@ jacobi_tc_kernel(const __grid_constant__ JtMaps maps, const JtParams p) {
     }
   }
 
-  if (MODE == JT_UPDATE && warp >= 2 && lane == 0) tma_store_wait_all();
+  if (Cfg::IS_UPDATE && warp >= 2 && lane == 0) tma_store_wait_all();
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) {
