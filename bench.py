@@ -524,7 +524,14 @@ def run_ours(a):
             line["cpu_baseline"] = cpu_baseline_entry(a)
         print(json.dumps(line))
     if world > 1:
-        td.barrier()
+        # the other ranks wait for rank 0's baseline legs on the rendezvous store (a blocking socket read): a NCCL
+        # barrier would have them spin on the host cores the CPU baseline is timed on
+        import datetime
+        store = td.distributed_c10d._get_default_store()
+        if rank == 0:
+            store.set("grasp_bench_done", "1")
+        else:
+            store.wait(["grasp_bench_done"], datetime.timedelta(minutes=30))
         td.destroy_process_group()
 
 
