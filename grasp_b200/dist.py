@@ -29,9 +29,33 @@ def rank_world() -> Tuple[int, int]:
 
 
 def svd_cost(m: int, n: int) -> float:
-    """Nominal thin-SVD work 8 m n^2 + 4/3 n^3 with n = min side."""
+    """Nominal thin-SVD work 8 m n^2 + 4/3 n^3 with n = min side: the figure the
+    roofline arithmetic uses."""
     big, small = max(m, n), min(m, n)
     return 8.0 * big * small * small + 4.0 / 3.0 * small ** 3
+
+
+def svd_working_shape(m: int, n: int) -> Tuple[int, int]:
+    """(rows, row length) the Jacobi phase of grasp_svd_batched works on: wide / tall matrices with a short side
+    >= 512 and a long side >= 1.5 x that are first reduced to their square CholeskyQR factor (csrc/svd_jacobi.cu,
+    pre_eligible).  Matrices of equal working shape share launches."""
+    r, L = min(m, n), max(m, n)
+    if r >= 512 and 2 * L >= 3 * r:
+        return r, r
+    return r, L
+
+
+def svd_time_cost(m: int, n: int) -> float:
+    """What the block-Jacobi SVD actually costs, up to a constant: rounds ~ r, bytes per round ~ r (L' + r), plus the
+    GEMMs of the preconditioning over the long side (measured: 4096 x 11008 takes 1.08x a 4096 x 4096).  The
+    nominal flop count would rate the MLP matrices 2.45x an attention matrix and leave the ranks that own attention
+    matrices with twice the work."""
+    r, L = min(m, n), max(m, n)
+    rw, Lw = svd_working_shape(m, n)
+    cost = float(rw) * rw * (Lw + rw)
+    if (rw, Lw) != (r, L):
+        cost += 0.04 * float(r) * r * L
+    return cost
 
 
 def partition_lpt(costs: Sequence[float], n_parts: int) -> List[List[int]]:
@@ -50,7 +74,7 @@ def partition_lpt(costs: Sequence[float], n_parts: int) -> List[List[int]]:
 def owners_of(shapes: Sequence[Tuple[int, int]], world: int) -> List[int]:
     """Owner rank of every matrix."""
     owner = [0] * len(shapes)
-    for r, items in enumerate(partition_lpt([svd_cost(m, n) for m, n in shapes], world)):
+    for r, items in enumerate(partition_lpt([svd_time_cost(m, n) for m, n in shapes], world)):
         for i in items:
             owner[i] = r
     return owner

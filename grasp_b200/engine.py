@@ -100,9 +100,11 @@ class SvdNotConverged(RuntimeError):
 
 
 def _batched_svd_local(weights: Sequence[torch.Tensor], max_group: int = 8):
+    # one call per WORKING shape: a preconditioned 11008 x 4096 matrix runs its Jacobi phase on a 4096 x 4096 factor
+    # and shares launches with the attention projections
     groups: "OrderedDict[tuple, list]" = OrderedDict()
     for i, w in enumerate(weights):
-        groups.setdefault(tuple(w.shape), []).append(i)
+        groups.setdefault(dist.svd_working_shape(*w.shape), []).append(i)
     out = [None] * len(weights)
     infos = []
     for idxs in groups.values():
