@@ -1297,12 +1297,13 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
     if (g.p >= 2) {
       const int tc_grid_g = min(sm_count(), g.nmat * P.ntiles * g.nsplit);
       const int tc_grid_u = min(sm_count(), g.nmat * P.ntiles * (g.ldz / 128));
-      // two-plane updates in the first sweeps (cyclic Jacobi needs ~log2(blocks) + 8 sweeps; the first log2(blocks) - 1
-      // are far from convergence).  GRASP_SVD_2PLANE_SWEEPS overrides (0 = three planes throughout, round 1).
+      // Two-plane updates (JT_UPDATE2: 8 instead of 12 bytes per element and round) in the first sweeps were
+      // measured and rejected: six such sweeps at n = 4096 leave QT orthogonal to ~1e-2 only, beyond what the single
+      // Newton-Schulz step of the clean-up repairs -- sigma error 4.4e-5 instead of 2e-7, reconstruction 8.8e-5
+      // instead of 1.8e-6, and two more sweeps (profiles/r02_svd_times_two_plane_sweeps.txt).  Off unless
+      // GRASP_SVD_2PLANE_SWEEPS=n asks for n of them.
       int two_plane_sweeps = 0;
       if (use_tc) {
-        for (int q = g.p; q > 2; q >>= 1) ++two_plane_sweeps;
-        if (two_plane_sweeps > 6) two_plane_sweeps = 6;
         if (const char* e = getenv("GRASP_SVD_2PLANE_SWEEPS")) two_plane_sweeps = atoi(e);
       }
       for (int sweep = 0; sweep < max_sweeps; ++sweep) {

@@ -48,9 +48,8 @@ template <int MODE>
 struct JtCfg {
   // the Gram only steers the rotations of a phase that stops at 1e-4: two planes / three products
   // (bf16x3, 4e-6) are plenty there; the update keeps all three planes (six products)
-  // JT_UPDATE2: while the off-diagonals are still large the third plane (bits 17..24) of Z and of the rotations buys
-  // nothing -- the clean-up stage recomputes Y = QT Y0 and re-orthogonalises QT anyway -- so the early sweeps read and
-  // write two planes: 8 instead of 12 bytes per element and round of the HBM-bound update.
+  // JT_UPDATE2 (experiment, off by default -- see grasp_svd_batched): the early sweeps read and write two planes only,
+  // 8 instead of 12 bytes per element and round of the HBM-bound update.
   static constexpr bool IS_GRAM = (MODE == JT_GRAM || MODE == JT_GRAM3);
   static constexpr bool IS_UPDATE = !IS_GRAM;
   static constexpr int GRAM_PLANES = (MODE == JT_GRAM) ? 2 : 3;
