@@ -1027,15 +1027,16 @@ static int gemm_kgroup(int ns, int K) {
 }
 
 // M blocks per super-row of the tile order: as many as keep their A planes (128 x K x NS x 2 bytes each) within
-// ~24 MB of the 126 MB L2, at least 4, and a whole number of waves where possible.  GRASP_GEMM_GROUP_M overrides
-// (a value >= tiles_m restores the round-1 M-fastest order).
+// 32 MB of the 126 MB L2, at least 4.  Measured DRAM reads of x[8176,4096] W[11008,4096]^T (ncu, 0.31 GB of operands,
+// profiles/r02_gemm_group_m_traffic.txt): 12 blocks 1.63 GB, 16 blocks 1.44 GB, 24 blocks 1.47 GB, 32 blocks 1.77 GB,
+// all 64 (the round-1 M-fastest order) 2.80 GB.  GRASP_GEMM_GROUP_M overrides.
 static int raster_group_m(int tiles_m, int tiles_n, int K, int ns) {
   static int forced = -1;
   if (forced < 0) { const char* e = getenv("GRASP_GEMM_GROUP_M"); forced = e ? atoi(e) : 0; }
   if (forced > 0) return forced < tiles_m ? forced : tiles_m;
   (void)tiles_n;
   const double per_block = 128.0 * (double)kp_of(K) * ns * 2.0;
-  int g = (int)(24.0 * 1024 * 1024 / per_block);
+  int g = (int)(32.0 * 1024 * 1024 / per_block);
   if (g < 4) g = 4;
   if (g > tiles_m) g = tiles_m;
   return g;

@@ -24,14 +24,16 @@ from . import dist, ops
 
 logger = logging.getLogger(__name__)
 
-# "torch": the three linear GEMMs of a GRASPLayer go through torch.matmul (cuBLAS fp32);
-# "grasp": they go through grasp_gemm_f32 (split-bf16 tcgen05 path of this library).
-_LINEAR_BACKEND = "torch"
+# The three GEMMs of a GRASPLayer used on its own (forward, dx, G = dY^T X):
+# "auto"  (default) grasp_gemm_f32 (tcgen05, fp16-plane arithmetic) for CUDA tensors; torch.matmul only for CPU
+#         tensors, which occur in the host-logic tests alone
+# "grasp" always grasp_gemm_f32;  "torch" always torch.matmul (cuBLAS fp32 on CUDA: the cross-check of the tests)
+_LINEAR_BACKEND = "auto"
 
 
 def set_linear_backend(name: str) -> None:
     global _LINEAR_BACKEND
-    if name not in ("torch", "grasp"):
+    if name not in ("auto", "torch", "grasp"):
         raise ValueError(name)
     _LINEAR_BACKEND = name
 
@@ -41,7 +43,7 @@ def linear_backend() -> str:
 
 
 def _mm(a: torch.Tensor, b: torch.Tensor, ta=False, tb=False, out=None, accumulate=False) -> torch.Tensor:
-    if _LINEAR_BACKEND == "grasp":
+    if _LINEAR_BACKEND == "grasp" or (_LINEAR_BACKEND == "auto" and a.is_cuda and a.dtype == torch.float32):
         return ops.gemm(a, b, ta=ta, tb=tb, beta=1.0 if accumulate else 0.0, C_out=out)
     A = a.t() if ta else a
     B = b.t() if tb else b
