@@ -219,19 +219,19 @@ def parse_args(argv=None):
 
 
 def _calibration_dataloader(args, tokenizer):
-    if args.dataset_name == "synthetic":
-        from grasp_b200 import synth
-        vocab = getattr(tokenizer, "vocab_size", None) or 32000
-        return synth.calibration_dataloader(args.num_samples, args.seq_len, vocab, batch_size=args.batch_size)
-    try:
-        from dataset.loader import get_calibration_dataloader  # the reference's loader (needs datasets on disk)
-    except ImportError as exc:
-        raise NotImplementedError(
-            "real calibration datasets are outside the hot path: use --dataset_name synthetic or put the "
-            "reference's dataset/loader.py (and its on-disk datasets) on PYTHONPATH") from exc
-    return get_calibration_dataloader(dataset_name=args.dataset_name, tokenizer=tokenizer,
-                                      num_samples=args.num_samples, batch_size=args.batch_size,
-                                      seq_len=args.seq_len, padding=args.padding)
+    """Batches in the reference loader's format (dataset/loader.py): the reference's own loader when it is importable,
+    else grasp_b200.loader (same sampling, chunking and batch format; corpora read from ./datasets as there)."""
+    if args.dataset_name != "synthetic":
+        try:
+            from dataset.loader import get_calibration_dataloader  # the reference's loader, if on PYTHONPATH
+            return get_calibration_dataloader(dataset_name=args.dataset_name, tokenizer=tokenizer,
+                                              num_samples=args.num_samples, batch_size=args.batch_size,
+                                              seq_len=args.seq_len, padding=args.padding)
+        except ImportError:
+            pass
+    from grasp_b200.loader import get_calibration_dataloader
+    return get_calibration_dataloader(dataset_name=args.dataset_name, tokenizer=tokenizer, num_samples=args.num_samples,
+                                      batch_size=args.batch_size, seq_len=args.seq_len, padding=args.padding)
 
 
 if __name__ == "__main__":
