@@ -58,6 +58,32 @@ def test_attention_forward_and_backward_match_fp64(cuda, parity_log, B, S, H, Hk
         assert errs["dq"] < 1e-5 and errs["dk"] < 1e-5 and errs["dv"] < 1e-5
 
 
+def test_attention_with_massive_activations(cuda, parity_log):
+    """Trained LLaMAs carry a few hidden dimensions / tokens 100-1000x larger than the rest.  The operands carry one
+    power-of-two scale per tensor, so the small entries keep fewer bits; the outputs must still be fp32-class
+    relative to their own scale (error measured against the largest entry of each result)."""
+    from grasp_b200 import ops
+    B, S, H, Hkv, D = 1, 300, 4, 2, 128
+    g = torch.Generator().manual_seed(77)
+    q = torch.randn(B * S, H * D, generator=g)
+    k = torch.randn(B * S, Hkv * D, generator=g)
+    v = torch.randn(B * S, Hkv * D, generator=g)
+    q[:, 5] *= 100.0; k[:, 5] *= 60.0                   # an outlier dimension shared by q and k (peaky attention)
+    v[0] *= 1000.0                                      # the attention-sink token
+    v[:, 200] *= 300.0
+    d_out = torch.randn(B * S, H * D, generator=g) * 1e-3
+    d_out[17] *= 500.0
+    q, k, v, d_out = (t.to(cuda) for t in (q, k, v, d_out))
+    scale = 1.0 / math.sqrt(D)
+    out, ctx = ops.attn_fwd(q, k, v, B, S, H, Hkv, D, scale)
+    dq, dk, dv = ops.attn_bwd(ctx, d_out)
+    o_ref, dq_ref, dk_ref, dv_ref, _ = reference(q, k, v, d_out, B, S, H, Hkv, D, scale)
+    errs = {"out": rel(out, o_ref), "dq": rel(dq, dq_ref), "dk": rel(dk, dk_ref), "dv": rel(dv, dv_ref)}
+    parity_log("attention with 100-1000x outliers: " + ", ".join(f"{n} {e:.1e}" for n, e in errs.items()))
+    assert all(torch.isfinite(t).all() for t in (out, dq, dk, dv))
+    assert errs["out"] < 5e-6 and max(errs["dq"], errs["dk"], errs["dv"]) < 5e-5
+
+
 @pytest.mark.parametrize("B,S,H,Hkv,D", [(2, 70, 4, 2, 64), (1, 511, 2, 2, 128)])
 def test_rope_and_operand_planes_in_one_preparation(cuda, B, S, H, Hkv, D):
     """grasp_attn_prep_qkv (RoPE + tensor-scaled planes in two passes, fp32 q / k untouched) feeds the same attention
