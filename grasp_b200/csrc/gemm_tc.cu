@@ -996,10 +996,13 @@ static bool wide_tiles(int64_t M, int64_t N, int64_t K = 1 << 20) {
   if (forced == 128) return false;
   if (forced == 256) return N > 128;
   if (N <= 128) return false;
-  // short K (the rank-k factors of compressed layers): a tile lives for a few K blocks only, so the time goes
-  // to its epilogue; 128-wide tiles have a 3-deep operand ring and twice the tiles to balance (measured 8-14 %
-  // faster for K <= 298, N >= 4096: profiles/r01_gemm_tile_width_short_k.txt)
-  if (K <= 512 && N > 256) return false;
+  // short K (the rank-k factors of compressed layers): with the staged epilogue and two K blocks per drain the
+  // 256-wide tile is 8-17 % faster there as well (N >= 4096, K = 204 / 298: profiles/r02_gemm_shapes_tile_width.txt;
+  // round 1's per-lane row stores made it the slower one), so the wave model below decides for every K.
+  // GRASP_GEMM_SHORTK_NARROW=1 restores the 128-wide choice.
+  static int narrow_short_k = -1;
+  if (narrow_short_k < 0) { const char* e = getenv("GRASP_GEMM_SHORTK_NARROW"); narrow_short_k = e ? atoi(e) : 0; }
+  if (narrow_short_k && K <= 512 && N > 256) return false;
   const int64_t sms = sm_count();
   const int64_t tm = ceil_div(M, TC_BM);
   const double c128 = (double)ceil_div(tm * ceil_div(N, 128), sms);
