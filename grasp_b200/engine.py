@@ -110,6 +110,9 @@ def _batched_svd_local(weights: Sequence[torch.Tensor], max_group: int = 8):
     out = [None] * len(weights)
     infos = []
     for idxs in groups.values():
+        # same ACTUAL shape side by side: a call whose matrices leave the tensor-core phase in the same sweep wastes
+        # no sweeps on the early ones (mixed groups of 8: 292 ms per matrix, pure ones 268-289; profiles/r02_svd_batch_sizes.txt)
+        idxs = sorted(idxs, key=lambda i: tuple(weights[i].shape))
         for s in range(0, len(idxs), max_group):
             chunk = idxs[s:s + max_group]
             usvs, info = ops.svd_batched([weights[i] for i in chunk], return_info=True)
