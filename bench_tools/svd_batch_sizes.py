@@ -21,6 +21,7 @@ for b in sizes:
     (outs, info), ms = ev(lambda: ops.svd_batched(mats, return_info=True))
     info = info.cpu()
     print(f"batch {b:3d}: {ms:8.1f} ms total, {ms / b:7.1f} ms per matrix; sweeps {sorted(set(info[:, 0].tolist()))} "
+          f"(per matrix {[(shapes[i][0] // 1000, int(info[i, 3]), int(info[i, 0])) for i in range(b)] if b <= 16 else ''}) "
           f"converged {int(info[:, 1].min())}; peak extra memory {(torch.cuda.max_memory_allocated() - base) / 2**30:.1f} GiB", flush=True)
     del outs, mats
     torch.cuda.empty_cache()
