@@ -118,3 +118,52 @@ def test_runner_refuses_other_model_families_and_masked_labels_average_like_hf()
         ours = runner.loss_sum(hidden, labels, torch.ones(2))
         ref = sum(model(input_ids=ids[i:i + 1], labels=labels[i:i + 1], use_cache=False)[0].item() for i in range(2))
     assert abs(ours.item() - ref) < 1e-4
+
+
+def test_svd_host_logic_groups_by_working_shape_and_climbs_the_retry_ladder(monkeypatch):
+    """engine._batched_svd_local (the host side of reference modeling_grasp.py:231 for many matrices): one library call
+    per group of <= 8 matrices with the same WORKING shape, same actual shapes side by side, results in input order,
+    and the recovery of a matrix the library flags (info[:, 1] == 0): as it is, then on the fp32 path, then refused.
+    The library call is replaced by a stand-in here (LAPACK on CPU) -- this tests the host logic, not a kernel."""
+    import pytest
+    from grasp_b200 import ops
+    calls = []
+    flagged = {"mode": None}
+
+    def fake_svd_batched(mats, prec=None, max_sweeps=0, return_info=False, precondition=True):
+        calls.append({"shapes": [tuple(m.shape) for m in mats], "prec": prec, "precondition": precondition,
+                      "max_sweeps": max_sweeps})
+        out = [tuple(torch.linalg.svd(m.double(), full_matrices=False)) for m in mats]
+        out = [tuple(t.float() for t in usv) for usv in out]
+        info = torch.zeros(len(mats), 4, dtype=torch.int32)
+        info[:, 0] = 15
+        for j, m in enumerate(mats):
+            bad = flagged["mode"] is not None and m.shape == (16, 8) and m[0, 0].item() == 7.0
+            ok = not bad or (flagged["mode"] == "precond" and not precondition) or \
+                (flagged["mode"] == "fp32" and prec == ops.PREC_SIMT)
+            info[j, 1] = int(ok)
+        return out, info
+
+    monkeypatch.setattr(ops, "svd_batched", fake_svd_batched)
+    g = torch.Generator().manual_seed(0)
+    # working shape (dist.svd_working_shape) = (short side, long side): tall and wide matrices share a group
+    shapes = [(16, 8)] * 5 + [(8, 8)] * 9 + [(8, 16)] * 2 + [(16, 8)] * 4
+    mats = [torch.randn(s, generator=g) for s in shapes]
+    mats[2][0, 0] = 7.0                                   # the matrix the stand-in will flag
+    out = engine._batched_svd_local(mats)
+    assert [c["shapes"] for c in calls] == [[(8, 16)] * 2 + [(16, 8)] * 6, [(16, 8)] * 3, [(8, 8)] * 8, [(8, 8)]]
+    for w, (U, S, Vh) in zip(mats, out):                  # input order survives the grouping
+        assert U.shape == (w.shape[0], min(w.shape)) and torch.allclose((U * S) @ Vh, w, atol=1e-5)
+
+    for mode, expect in (("precond", [False]), ("fp32", [False, True])):
+        calls.clear(); flagged["mode"] = mode
+        out = engine._batched_svd_local(mats)
+        retries = [c for c in calls if c["shapes"] == [(16, 8)] and len(c["shapes"]) == 1 and
+                   (not c["precondition"] or c["prec"] == ops.PREC_SIMT)]
+        assert [c["precondition"] for c in retries] == expect
+        if mode == "fp32":
+            assert retries[-1]["prec"] == ops.PREC_SIMT and retries[-1]["max_sweeps"] == 48
+        assert torch.allclose((out[2][0] * out[2][1]) @ out[2][2], mats[2], atol=1e-5)
+    flagged["mode"] = "never"
+    with pytest.raises(engine.SvdNotConverged):
+        engine._batched_svd_local(mats)
