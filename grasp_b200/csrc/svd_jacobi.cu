@@ -1416,10 +1416,13 @@ extern "C" int grasp_svd_batched(int batch, const float* const* A, const int64_t
             }
           }
           GRASP_LAUNCH(svd_sweep_end_kernel, dim3(1), dim3(32), 0, st, g, sweep, cleanup_conv, s2);
-          if (s2 == 0 && !tc_cleanup && gemm_check) {
+          if (s2 + 1 < extra && !tc_cleanup && gemm_check) {
             // A sweep only knows the off-diagonals it met BEFORE rotating them, so confirming convergence costs
             // another full sweep (Gram + eigen-solve of every pair, ~45% of a sweep).  The whole Gram as one
             // fp32-class tensor-core GEMM plus a max-reduction gives the same answer for ~1 ms per matrix.
+            // Also after the second sweep: about a third of the 4096 x 4096 matrices leave the tensor-core phase just
+            // under its 1e-4 bar and need two clean-up sweeps; without this check a third one would only confirm them
+            // (profiles/r02_svd_batch_sizes.txt: 16 + 3 sweeps).
             for (int j = 0; j < g.nmat && !rc; ++j) {
               const SvdPlan& Q = plans[members[j]];
               float* T = reinterpret_cast<float*>(base[members[j]] + Q.off_T);
