@@ -113,11 +113,13 @@ def golden_select(ref):
     torch.save(out, os.path.join(GOLDEN, "select_small.pt"))
 
 
-def run_reference(ref, model, tokens, num_prune_layers, ratio, merge):
+def run_reference(ref, model, tokens, num_prune_layers, ratio, merge, metric="taylor", threshold_ratio=None,
+                  angular=False):
     """The reference's own GRASPModel methods in grasp.main order (grasp.py:61-126), CPU."""
     batches = restate.batches_from_tokens(tokens)
     gm = ref.modeling.GRASPModel(model)
-    imp, layers = gm.compute_bi(num_prune_layers=num_prune_layers, calibration_dataloader=batches, device="cpu")
+    imp, layers = gm.compute_bi(num_prune_layers=num_prune_layers, calibration_dataloader=batches, angular=angular,
+                                device="cpu")
     rec = {"layer_importances": list(imp), "layers_id": sorted(layers, reverse=True), "blocks": []}
     for lid in rec["layers_id"]:
         for block_type, types in (("mlp", ["down_proj", "up_proj", "gate_proj"]),
@@ -126,11 +128,12 @@ def run_reference(ref, model, tokens, num_prune_layers, ratio, merge):
             names = gm.check_exists_grasp_layer()
             S = {n: gm.model.get_submodule(n).S.data.clone() for n in names}
             grads = gm.get_svdlayer_gradients(batches, "cpu")
-            idx = gm.dynamic_svd_selection(grads, metric="taylor", compression_ratio=ratio)
+            idx = gm.dynamic_svd_selection(grads, metric=metric, compression_ratio=ratio, threshold_ratio=threshold_ratio)
             rec["blocks"].append({"layer": lid, "block": block_type, "names": names, "S": S,
                                   "grads": {n: grads[n].clone() for n in names},
-                                  "scores": {n: torch.abs(grads[n] * S[n]) for n in names},
-                                  "indices": {n: idx[n].clone() for n in names}})
+                                  "scores": {n: torch.abs(grads[n] * S[n]) if metric == "taylor" else torch.abs(grads[n])
+                                             for n in names},
+                                  "indices": {n: torch.as_tensor(idx[n]).clone() for n in names}})
             gm.compile_grasp_model(idx, merge=merge, device="cpu")
     return gm, rec
 
@@ -165,15 +168,69 @@ def golden_e2e(ref, name, n_samples, seq_len, num_prune_layers, ratio, fname):
     torch.save(fixture, os.path.join(GOLDEN, fname))
 
 
+VARIANTS = {
+    # the option branches of the same path: the |gradient| score (modeling_grasp.py:393-394); rank chosen by the
+    # cumulative-score threshold (:408-410) with merged rebuild.  (compute_bi(angular=True) cannot be pinned: the
+    # reference's own branch raises UnboundLocalError at :154; block_influence(angular=True) itself is in bi_small.pt.)
+    "gradient_metric": dict(num_prune_layers=2, ratio=0.5, merge=False, metric="gradient", threshold_ratio=None,
+                            angular=False),
+    "threshold_merge": dict(num_prune_layers=1, ratio=None, merge=True, metric="taylor", threshold_ratio=0.7,
+                            angular=False),
+}
+
+
+def golden_e2e_variants(ref, fname="e2e_tiny_variants.pt"):
+    name = "tiny"
+    tokens = synth.random_tokens(6, 33, synth.MODEL_CONFIGS[name]["vocab_size"], seed=1)
+    model = synth.random_llama(name, seed=0)
+    fixture = {"model": name, "seed": 0, "tokens": tokens, "model_sha256": state_checksum(model), "variants": {}}
+    for vname, kw in VARIANTS.items():
+        gm, rec = run_reference(ref, copy.deepcopy(model), tokens, kw["num_prune_layers"], kw["ratio"], kw["merge"],
+                                metric=kw["metric"], threshold_ratio=kw["threshold_ratio"], angular=kw["angular"])
+        rec["options"] = dict(kw)
+        rec["ppl_compressed"] = restate.perplexity(gm.model, tokens)
+        rec["final_state"] = {k: v.clone() for k, v in gm.model.state_dict().items()
+                              if any(f"layers.{l}." in k for l in rec["layers_id"])}
+        rec2 = restate.run_grasp(copy.deepcopy(model), tokens, num_prune_layers=kw["num_prune_layers"],
+                                 compression_ratio=kw["ratio"], metric=kw["metric"], merge=kw["merge"],
+                                 threshold_ratio=kw["threshold_ratio"])
+        assert rec2["layers_id"] == rec["layers_id"], (rec2["layers_id"], rec["layers_id"])
+        close(rec2["layer_importances"], rec["layer_importances"], 1e-5, "BI")
+        for b_ref, b_re in zip(rec["blocks"], rec2["blocks"]):
+            for n in b_ref["names"]:
+                close(b_re["S"][n], b_ref["S"][n], 1e-6, f"S {n}")
+                close(b_re["grads"][n], b_ref["grads"][n], 1e-4, f"grad {n}")
+                assert set(b_re["indices"][n].tolist()) == set(b_ref["indices"][n].tolist()), n
+        fixture["variants"][vname] = rec
+        print(f"{fname} {vname}: layers {rec['layers_id']} ranks "
+              f"{[len(b['indices'][n]) for b in rec['blocks'] for n in b['names']]} ppl {rec['ppl_compressed']:.3f}")
+    # SVDLinear's other sigma placements (modeling_grasp.py:49-54)
+    g = torch.Generator().manual_seed(5)
+    U, S, Vh = torch.linalg.svd(torch.randn(48, 80, generator=g), full_matrices=False)
+    idx = torch.tensor([0, 3, 4, 9, 17])
+    fuse = {}
+    for mode in ("U", "V"):
+        m = ref.modeling.SVDLinear(U[:, idx], S[idx], Vh[idx, :], None, mode)
+        fuse[mode] = {"in_w": m.InLinear.weight.data.clone()}
+        if mode == "U":
+            fuse[mode]["out_w"] = m.OutLinear.weight.data.clone()
+    fixture["sigma_fuse"] = {"U": U[:, idx].clone(), "S": S[idx].clone(), "Vh": Vh[idx, :].clone(), "modes": fuse}
+    torch.save(fixture, os.path.join(GOLDEN, fname))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(min(8, os.cpu_count() or 1))
     ref = ref_import.load()
+    if "variants" in sys.argv[1:]:      # only the option-variant fixture (the others stay byte-identical)
+        golden_e2e_variants(ref)
+        return
     golden_bi(ref)
     golden_svd()
     golden_select(ref)
     golden_e2e(ref, "tiny", n_samples=6, seq_len=33, num_prune_layers=2, ratio=0.5, fname="e2e_tiny.pt")
     golden_e2e(ref, "small", n_samples=4, seq_len=65, num_prune_layers=2, ratio=0.8, fname="e2e_small.pt")
+    golden_e2e_variants(ref)
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)) // 1024, "KiB")
 

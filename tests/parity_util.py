@@ -24,9 +24,11 @@ def jaccard(a, b):
     return len(a & b) / max(len(a | b), 1)
 
 
-def compare_blocks(rec, ref, log=None, tag=""):
+def compare_blocks(rec, ref, log=None, tag="", metric="taylor", adaptive=False):
     """rec / ref: {"blocks": [{"names", "S", "grads", "indices"(, "scores")}]} of ours and of the reference.
-    Returns the worst figures; asserts the bars."""
+    Returns the worst figures; asserts the bars.  metric: the score the run selected by (modeling_grasp.py:393-396).
+    adaptive: ranks chosen by the cumulative-score threshold (:408-410) -- the count itself is then data dependent and
+    may move by one where the running sum meets the target."""
     worst = {"sigma": 0.0, "sigma_rel": 0.0, "jaccard": 1.0, "tie": 0.0, "score": 0.0, "swapped": 0, "kept": 0}
     for b, br in zip(rec["blocks"], ref["blocks"]):
         assert b["names"] == br["names"]
@@ -35,10 +37,10 @@ def compare_blocks(rec, ref, log=None, tag=""):
             worst["sigma"] = max(worst["sigma"], ((S - Sr).abs().max() / Sr[0]).item())
             big = Sr >= 1e-3 * Sr[0]
             worst["sigma_rel"] = max(worst["sigma_rel"], ((S - Sr).abs()[big] / Sr[big]).max().item())
-            score = (b["grads"][n].cpu() * S).abs()
+            score = (b["grads"][n].cpu() * S).abs() if metric == "taylor" else b["grads"][n].cpu().abs()
             score_ref = br["scores"][n].cpu() if "scores" in br else (br["grads"][n].cpu() * Sr).abs()
             ours, theirs = b["indices"][n].tolist(), br["indices"][n].tolist()
-            assert len(ours) == len(theirs), n
+            assert abs(len(ours) - len(theirs)) <= (1 if adaptive else 0), (n, len(ours), len(theirs))
             kth = score_ref[theirs[-1]].item() if theirs else 0.0
             for i in set(ours) ^ set(theirs):
                 worst["tie"] = max(worst["tie"], abs(score_ref[i].item() - kth) / max(kth, 1e-30))

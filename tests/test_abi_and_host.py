@@ -135,3 +135,15 @@ def test_synthetic_loader_has_the_reference_batch_format():
     assert b["input_ids"].shape == (2, 15) and b["labels"].shape == (2, 15)
     toks = synth.random_tokens(5, 16, 100)
     assert torch.equal(b["input_ids"], toks[:2, :-1]) and torch.equal(b["labels"], toks[:2, 1:])
+
+
+def test_sigma_fuse_placements_match_the_reference(golden):
+    """SVDLinear with the singular values on one side only (modeling_grasp.py:49-54), against the reference's module.
+    "V" leaves OutLinear at its default initialisation there and here, so only InLinear is compared."""
+    from modeling_grasp import SVDLinear
+    fx = golden("e2e_tiny_variants.pt")["sigma_fuse"]
+    for mode, want in fx["modes"].items():
+        m = SVDLinear(fx["U"], fx["S"], fx["Vh"], None, mode)
+        assert torch.equal(m.InLinear.weight.data, want["in_w"])
+        if "out_w" in want:
+            assert torch.equal(m.OutLinear.weight.data, want["out_w"])

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 from parity_util import compare_blocks, compare_final_weights, rel
 
 
-def run_ours(model, tokens, num_prune_layers, ratio, merge, device, use_engine=True):
+def run_ours(model, tokens, num_prune_layers, ratio, merge, device, use_engine=True, **options):
     """grasp.compress with per-block artefacts captured from the public GRASPModel methods."""
     import grasp
     from modeling_grasp import GRASPModel
@@ -36,7 +36,8 @@ def run_ours(model, tokens, num_prune_layers, ratio, merge, device, use_engine=T
 
     gm.dynamic_svd_selection = spy
     dl = synth.calibration_dataloader(0, 0, 0, tokens=tokens)
-    grasp.compress(gm, dl, num_prune_layers=num_prune_layers, compression_ratio=ratio, merge=merge, device=device)
+    grasp.compress(gm, dl, num_prune_layers=num_prune_layers, compression_ratio=ratio, merge=merge, device=device,
+                   **options)
     rec["layer_importances"] = gm.layer_importances
     rec["layers_id"] = gm.redundant_layers
     return gm, rec
@@ -71,6 +72,30 @@ def test_end_to_end_parity_with_reference(cuda, golden, parity_log, fname, merge
     ppl = restate.perplexity(gm.model, fx["tokens"])
     assert abs(ppl - ref["ppl_compressed"]) / ref["ppl_compressed"] < 5e-3, (ppl, ref["ppl_compressed"])
     assert abs(restate.perplexity(dense, fx["tokens"]) - ref["ppl_dense"]) / ref["ppl_dense"] < 1e-4
+
+
+@pytest.mark.parametrize("variant", ["gradient_metric", "threshold_merge"])
+def test_option_variants_match_the_reference(cuda, golden, parity_log, variant):
+    """The option branches of the path, against runs of the reference with the same options
+    (tests/golden/e2e_tiny_variants.pt, oracle/make_golden.py:VARIANTS): the |gradient| score (modeling_grasp.py:393-394)
+    and ranks chosen by the cumulative-score threshold (:408-410, tools/utils_func.py:45-57) with the merged rebuild."""
+    fx = golden("e2e_tiny_variants.pt")
+    ref = fx["variants"][variant]
+    opt = ref["options"]
+    model = synth.random_llama(fx["model"], seed=fx["seed"])
+    assert state_checksum(model) == fx["model_sha256"]
+    dense = copy.deepcopy(model)
+    gm, rec = run_ours(model, fx["tokens"], opt["num_prune_layers"], opt["ratio"], opt["merge"], "cuda",
+                       metric=opt["metric"], threshold_ratio=opt["threshold_ratio"])
+    tag = f"e2e variant {variant}"
+    assert rec["layers_id"] == ref["layers_id"]
+    assert rel(rec["layer_importances"], ref["layer_importances"]) < 1e-4
+    compare_blocks(rec, ref, parity_log, tag, metric=opt["metric"], adaptive=opt["threshold_ratio"] is not None)
+    ours_sd = {k: v.detach().cpu() for k, v in gm.model.state_dict().items()}
+    compare_final_weights(rec, ref, ours_sd, ref["final_state"], dense.state_dict(), parity_log, tag)
+    gm.model.to("cpu")
+    ppl = restate.perplexity(gm.model, fx["tokens"])
+    assert abs(ppl - ref["ppl_compressed"]) / ref["ppl_compressed"] < 5e-3, (ppl, ref["ppl_compressed"])
 
 
 def test_grasp_layer_standalone_backward_matches_oracle(cuda):

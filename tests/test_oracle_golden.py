@@ -89,3 +89,24 @@ def test_end_to_end_restatement_matches_reference(golden, fname, merge):
             assert rel(b["S"][n], br["S"][n]) < 1e-6
             assert rel(b["grads"][n], br["grads"][n]) < 1e-4
             assert set(b["indices"][n].tolist()) == set(br["indices"][n].tolist())
+
+
+@pytest.mark.parametrize("variant", ["gradient_metric", "threshold_merge"])
+def test_option_variants_of_the_restatement_match_reference(golden, variant):
+    """|gradient| score and threshold-chosen ranks (modeling_grasp.py:393-394, 408-410) against the reference's runs."""
+    fx = golden("e2e_tiny_variants.pt")
+    ref = fx["variants"][variant]
+    opt = ref["options"]
+    model = synth.random_llama(fx["model"], seed=fx["seed"])
+    assert state_checksum(model) == fx["model_sha256"]
+    rec = restate.run_grasp(copy.deepcopy(model), fx["tokens"], num_prune_layers=opt["num_prune_layers"],
+                            compression_ratio=opt["ratio"], metric=opt["metric"], merge=opt["merge"],
+                            threshold_ratio=opt["threshold_ratio"])
+    assert rec["layers_id"] == ref["layers_id"]
+    for b, br in zip(rec["blocks"], ref["blocks"]):
+        assert b["names"] == br["names"]
+        for n in b["names"]:
+            assert rel(b["S"][n], br["S"][n]) < 1e-6
+            assert rel(b["grads"][n], br["grads"][n]) < 1e-4
+            assert rel(b["scores"][n], br["scores"][n]) < 1e-4
+            assert b["indices"][n].tolist() == br["indices"][n].tolist()
