@@ -139,3 +139,39 @@ def test_unsupported_modules_fall_back():
     assert not f.supported()
     # and the runner never picks the fused route for CPU tensors (the product backend is CUDA-only)
     assert runner.fused(torch.zeros(1, 4, 64)) is None
+
+
+def test_fused_pass_with_biased_linears():
+    """LlamaConfig(attention_bias=True, mlp_bias=True): dense linears above the block add their bias, a GRASPLayer
+    ignores its own (reference modeling_grasp.py:77-79), a compiled factor pair carries it on OutLinear (:41-44)."""
+    model = _model(11, attention_bias=True, mlp_bias=True)
+    g = torch.Generator().manual_seed(1)
+    for n, p in model.named_parameters():
+        if n.endswith(".bias"):
+            p.data = torch.randn(p.shape, generator=g) * 0.05      # HF initialises them to zero
+    _to_svdlinear(model, "model.layers.3.self_attn.v_proj", 7)
+    _to_svdlinear(model, "model.layers.3.mlp.gate_proj", 12)
+    names = [f"model.layers.1.self_attn.{t}" for t in ("q_proj", "k_proj", "v_proj", "o_proj")]
+    layers = {n: _to_grasp(model, n) for n in names}
+    assert all(l.bias is not None for l in layers.values())
+    runner = engine.LlamaRunner(model, micro_batch=2, use_grasp_gemm=False)
+    tokens = synth.random_tokens(2, 12, 256, seed=6)
+    ids, labels = tokens[:, :-1], tokens[:, 1:]
+    weights = torch.ones(2)
+    with torch.no_grad():
+        src = runner.hidden_states(ids)[1]
+        # the runner's layer-wise forward is HF's own forward, biases included
+        ref = model(input_ids=ids, output_hidden_states=True, use_cache=False, return_dict=True).hidden_states
+        assert torch.allclose(runner.hidden_states(ids)[-1], ref[-1], atol=2e-5, rtol=1e-5)
+    with engine.deferred_sigma_grads(layers.values()):
+        loss_ref = runner.loss_sum(runner.run_layers(src, 1, 4), labels, weights)
+        loss_ref.backward()
+        G_ref = {n: l._G.clone() for n, l in layers.items()}
+    f = FusedLlama(runner, TorchBackend())
+    assert f.supported()
+    with engine.deferred_sigma_grads(layers.values()), torch.no_grad():
+        loss = f.forward_backward(src, labels, weights, 1, 1)
+        G = {n: l._G.clone() for n, l in layers.items()}
+    assert abs(loss.item() - loss_ref.item()) < 1e-5
+    for n in layers:
+        assert (G[n] - G_ref[n]).abs().max().item() <= 2e-5 * G_ref[n].abs().max().item() + 1e-9, n
